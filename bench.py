@@ -1,0 +1,368 @@
+#!/usr/bin/env python
+"""Benchmark of the VoteNet point-cloud hot path (BASELINE.json: scenes/sec of the
+Pointnet2Backbone forward, 40k points, batch 16, at 1/2/4/8 B200).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+    torchrun --nnodes=1 --nproc-per-node N ... bench.py --gpus N --steps K --warmup W
+
+One "step" = one Pointnet2Backbone forward (SA1-4 + FP1-2, eval mode) over one batch of 16
+synthetic 40 000-point scenes with xyz + colour + normal + height (C = 7): BASELINE.json
+configs[1].  Scenes shard across GPUs by batch index, 16 per GPU (weak scaling, the
+reference's DDP recipe README.md:60-70); the forward needs no collective.
+
+Prints ONE JSON line (rank 0).  See DESIGN.md "Measurement" for every field.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+NUM_POINTS = 40000
+BATCH = 16
+FEATURES = 7
+METRIC = "scenes/sec VoteNet backbone fwd (40k pts, B=16)"
+UNIT = "scenes/s"
+WORKLOAD = "Pointnet2Backbone forward (SA1-4 2048/1024/512/256, FP1-2), 40000 pts xyz+color+normal+height (C=7), batch 16 per GPU, eval"
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        p = json.load(open(path))
+        return {"hbm_gbs": p["hbm_gbs"], "bf16_tflops": p["bf16_tflops"],
+                "bf16_tflops_sustained": p.get("bf16_tflops_sustained", p["bf16_tflops"]),
+                "source": "measured"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0,
+            "source": "fallback"}
+
+
+# --------------------------------------------------------------------------- clocks ---
+
+class ClockSampler(object):
+    """nvidia-smi sampled every 200 ms DURING the timed region (B200_PROFILING.md recipe)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.proc = None
+        self.path = None
+        self.index = index
+
+    def start(self):
+        try:
+            fd, self.path = tempfile.mkstemp(suffix=".csv")
+            os.close(fd)
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                 "--format=csv,noheader,nounits", "-lms", "200"],
+                stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.proc is None:
+            return out
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        try:
+            for line in open(self.path):
+                f = [x.strip() for x in line.split(",")]
+                if len(f) < 8:
+                    continue
+                try:
+                    sm.append(float(f[1]))
+                    mx.append(float(f[2]))
+                except ValueError:
+                    continue
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown",
+                                    "sw_power_cap"), f[4:8]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            os.unlink(self.path)
+        except Exception:
+            pass
+        if sm:
+            sm.sort()
+            out.update(sm_mhz=sm[len(sm) // 2], sm_max_mhz=max(mx), samples=len(sm))
+        out["reasons"] = sorted(reasons)
+        return out
+
+
+# ------------------------------------------------------------------ reference (CPU) ---
+
+def cpu_reference_run(steps, warmup, sample_scenes, threads=None):
+    """The reference path re-expressed on the host (the reference ops are CUDA-only,
+    sampling.cpp:83): C oracle ops + torch-CPU conv/BN, all host threads.  Each step is a
+    bounded sample of the workload: `sample_scenes` scenes of the same 40k-point config."""
+    import torch
+    from bridgeqa_b200 import detector, synthetic
+    from oracle import cpu_ops, modules_cpu
+    cores = threads or os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    cpu_ops.set_num_threads(cores)
+    net = synthetic.fill_state_dict(detector.Pointnet2Backbone(input_feature_dim=FEATURES), seed=0)
+    sd = net.state_dict()
+    pc = synthetic.make_batch(sample_scenes, NUM_POINTS, FEATURES).numpy()
+    for _ in range(warmup):
+        modules_cpu.backbone(pc[:1], sd)
+    times = []
+    for _ in range(steps):
+        t0 = time.perf_counter()
+        modules_cpu.backbone(pc, sd)
+        times.append(time.perf_counter() - t0)
+    total = sum(times)
+    return {"value": sample_scenes * steps / total, "ms_per_step": 1e3 * total / steps,
+            "cores": cores, "sample": "%d scene(s) of the workload per step, %d step(s)" % (sample_scenes, steps)}
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    steps = max(1, min(args.steps, 3))
+    r = cpu_reference_run(steps, min(args.warmup, 1), sample_scenes=4)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus,
+        "steps": steps, "warmup": min(args.warmup, 1), "ms_per_step": r["ms_per_step"],
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic", "config": {"workload": WORKLOAD, "sample_scenes_per_step": 4},
+        "cpu_baseline": {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port",
+                         "sample": r["sample"]},
+        "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+        "note": "reference pointnet2 ops are CUDA-only; this is the line-by-line host port (oracle/) "
+                "timed on the box's CPU cores, per BASELINE.json north_star",
+    }
+    print(json.dumps(line))
+    return 0
+
+
+# ----------------------------------------------------------------------- product arm ---
+
+def algorithmic_work(name, dims):
+    """Algorithmic bytes (and flops) of one C-ABI call, from its integer arguments.
+    Formulas: DESIGN.md 'Kernels' / SURVEY.md 8d."""
+    if name == "bqa_furthest_point_sampling":
+        b, n, m = dims[:3]
+        return {"bytes": b * (12 * n + 4 * m + 12 * m), "bound": "hbm", "iters": m - 1, "units": b}
+    if name == "bqa_ball_query":
+        b, n, m, ns = dims[:4]
+        return {"bytes": b * (12 * n + 12 * m + 4 * m * ns), "bound": "hbm", "pair_tests": b * n * m}
+    if name in ("bqa_group_points", "bqa_group_points_grad"):
+        b, c, n, npt, ns = dims[:5]
+        return {"bytes": b * (4 * npt * ns + 8 * c * npt * ns), "bound": "hbm"}
+    if name in ("bqa_gather_points", "bqa_gather_points_grad"):
+        b, c, n, m = dims[:4]
+        return {"bytes": b * (4 * m + 8 * c * m), "bound": "hbm"}
+    if name == "bqa_three_nn":
+        b, n, m = dims[:3]
+        return {"bytes": b * (12 * n + 12 * m + 24 * n), "bound": "hbm"}
+    if name in ("bqa_three_interpolate", "bqa_three_interpolate_grad"):
+        b, c, m, n = dims[:4]
+        return {"bytes": b * (24 * n + 4 * c * m + 4 * c * n), "bound": "hbm"}
+    if name == "bqa_transpose_to_point_major":
+        b, c, n = dims[:3]
+        return {"bytes": 8 * b * c * n, "bound": "hbm"}
+    if name == "bqa_sa_mlp_max_forward":
+        b, n, npt, ns, c, c1, c2, c3 = dims[:8]
+        flops = 2 * b * npt * ns * ((c + 3) * c1 + c1 * c2 + c2 * c3)
+        byts = b * (4 * npt * ns + 4 * npt * ns * (c + 3) + 4 * c3 * npt)
+        return {"bytes": byts, "flops": flops, "bound": "tensor"}
+    if name == "bqa_fp_forward":
+        b, n, m, ck, cs, c1, c2 = dims[:7]
+        flops = 2 * b * n * ((ck + cs) * c1 + c1 * c2)
+        byts = 4 * b * (ck * m + cs * n + c2 * n + 3 * n + 3 * m)
+        return {"bytes": byts, "flops": flops, "bound": "tensor"}
+    return {"bytes": 0, "bound": "hbm"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--unfused", action="store_true", help="force the un-fused operator path")
+    ap.add_argument("--tf32", action="store_true", help="allow TF32 in torch convs of the un-fused path")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference_arm(args)
+
+    import torch
+    import torch.distributed as dist
+    import bridgeqa_b200
+    from bridgeqa_b200 import _native, detector, profiler, synthetic
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a GPU: the product path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    device = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=device)
+    args.warmup = max(args.warmup, 3)
+    if args.unfused:
+        bridgeqa_b200.set_fused(False)
+    torch.backends.cudnn.allow_tf32 = bool(args.tf32)
+    torch.backends.cuda.matmul.allow_tf32 = bool(args.tf32)
+
+    _native.lib()   # fail loudly here if the CUDA library is missing
+    net = synthetic.fill_state_dict(detector.Pointnet2Backbone(input_feature_dim=FEATURES), seed=0)
+    net = net.to(device).eval()
+
+    # inputs: 16 scenes per rank, resident in HBM in ROT rotated variants so that a step's
+    # input was last touched ROT-1 steps (and >> 126 MB of other traffic) ago
+    ROT = 6
+    host_batch = synthetic.make_batch(BATCH, NUM_POINTS, FEATURES, first_scene=rank * BATCH)
+    host_pinned = [torch.roll(host_batch, shifts=997 * i, dims=1).contiguous().pin_memory() for i in range(ROT)]
+    dev_inputs = [h.to(device) for h in host_pinned]
+    flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=device)
+
+    def step(i):
+        with torch.no_grad():
+            return net({"point_clouds": dev_inputs[i % ROT]})["fp2_features"]
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    for i in range(args.warmup):
+        step(i)
+    barrier()
+
+    # ---- timed region: exactly K steps, device-timed, per-kernel events recorded live ----
+    clocks = ClockSampler(local_rank)
+    if rank == 0:
+        clocks.start()
+    launches0 = _native.launch_count()
+    ev0 = torch.cuda.Event(enable_timing=True)
+    ev1 = torch.cuda.Event(enable_timing=True)
+    with profiler.KernelTimer() as kt:
+        ev0.record()
+        for i in range(args.steps):
+            step(i)
+        ev1.record()
+        barrier()
+    elapsed_ms = ev0.elapsed_time(ev1)
+    launches = _native.launch_count() - launches0
+    clk = clocks.stop() if rank == 0 else None
+    kern = kt.summary()
+
+    # ---- e2e: host (pinned) -> device -> forward -> host, copies inside the timed region ----
+    out_host = {
+        "fp2_features": torch.empty((BATCH, 256, 1024), dtype=torch.float32).pin_memory(),
+        "fp2_xyz": torch.empty((BATCH, 1024, 3), dtype=torch.float32).pin_memory(),
+        "fp2_inds": torch.empty((BATCH, 1024), dtype=torch.int32).pin_memory(),
+    }
+    h2d_bytes = host_pinned[0].numel() * 4
+    d2h_bytes = sum(t.numel() * t.element_size() for t in out_host.values())
+
+    def e2e_step(i):
+        with torch.no_grad():
+            pc = host_pinned[i % ROT].to(device, non_blocking=True)
+            dd = net({"point_clouds": pc})
+            for k, t in out_host.items():
+                t.copy_(dd[k], non_blocking=True)
+
+    for i in range(3):
+        e2e_step(i)
+    barrier()
+    e0 = torch.cuda.Event(enable_timing=True)
+    e1 = torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(args.steps):
+        e2e_step(i)
+    e1.record()
+    barrier()
+    e2e_ms = e0.elapsed_time(e1)
+
+    # max over ranks
+    t = torch.tensor([elapsed_ms, e2e_ms], dtype=torch.float64, device=device)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    elapsed_ms, e2e_ms = float(t[0]), float(t[1])
+
+    if rank == 0:
+        peaks = measured_peaks()
+        scenes = BATCH * world * args.steps
+        value = scenes / (elapsed_ms / 1e3)
+        kernels = []
+        for key, d in kern.items():
+            w = algorithmic_work(d["name"], d["dims"])
+            ms = d["ms"] / d["calls"]
+            row = {"kernel": d["name"], "dims": d["dims"], "calls_per_step": d["calls"] / args.steps,
+                   "ms": round(ms, 5), "share": round(d["ms"] / elapsed_ms, 4), "bound": w["bound"]}
+            if w["bound"] == "tensor":
+                ach = w["flops"] / (ms / 1e3) / 1e12
+                peak = peaks["bf16_tflops_sustained"]
+                row.update(achieved=round(ach, 2), peak=peak, unit="TFLOP/s", frac=round(ach / peak, 4))
+            else:
+                ach = w["bytes"] / (ms / 1e3) / 1e9
+                row.update(achieved=round(ach, 2), peak=peaks["hbm_gbs"], unit="GB/s",
+                           frac=round(ach / peaks["hbm_gbs"], 5))
+            if "iters" in w and w["iters"] > 0:
+                row["us_per_iter"] = round(1e3 * ms / w["iters"], 4)
+            if "pair_tests" in w:
+                row["gpairs_per_s"] = round(w["pair_tests"] / (ms / 1e3) / 1e9, 1)
+            kernels.append(row)
+        kernels.sort(key=lambda r: -r["share"])
+        top = kernels[0] if kernels else None
+        roofline = None
+        if top:
+            roofline = {"kernel": "%s%s" % (top["kernel"], top["dims"]), "bound": top["bound"],
+                        "achieved": top["achieved"], "peak": top["peak"], "unit": top["unit"],
+                        "frac": top["frac"], "traffic": None, "peak_source": peaks["source"],
+                        "share_of_step": top["share"], "ms": top["ms"]}
+            if "us_per_iter" in top:
+                roofline["us_per_iter"] = top["us_per_iter"]
+                roofline["note"] = ("FPS is a serial chain of npoint-1 cluster-wide argmax steps: "
+                                    "latency-bound, HBM fraction is reported for the contract only")
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None,
+            "dtype": "bf16" if any(r["kernel"] == "bqa_sa_mlp_max_forward" for r in kernels) else "f32",
+            "data": "synthetic",
+            "config": {"workload": WORKLOAD, "global_batch": BATCH * world, "num_points": NUM_POINTS,
+                       "parallelism": "scenes sharded by batch index, %d/GPU, no collective in forward" % BATCH,
+                       "l2": "inputs rotate over %d resident batches (%.0f MB) + >1 GB intermediate traffic per step"
+                             % (ROT, ROT * h2d_bytes / 1e6),
+                       "fused": any(r["bound"] == "tensor" for r in kernels), "torch_tf32": bool(args.tf32)},
+            "e2e": {"value": scenes / (e2e_ms / 1e3), "unit": UNIT, "ms_per_step": e2e_ms / args.steps,
+                    "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes},
+            "gpu_launches": launches,
+            "roofline": roofline,
+            "kernels": kernels,
+            "clocks": clk,
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            r = cpu_reference_run(steps=1, warmup=0, sample_scenes=4)
+            line["cpu_baseline"] = {"value": r["value"], "unit": UNIT, "cores": r["cores"],
+                                    "kind": "port", "sample": r["sample"]}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -1,0 +1,163 @@
+// api.cu -- the extern "C" surface declared in include/bqa_pointnet2.h.
+// Argument checks mirror the reference wrappers' intent (lib/pointnet2/_ext_src/src/
+// *.cpp) but report through a status code + bqa_last_error() instead of AT_ASSERT or
+// exit(-1) (cuda_utils.h:30-39).
+#include <atomic>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+
+#include "common.cuh"
+
+namespace bqa {
+
+static thread_local char g_err[512] = "";
+static std::atomic<long long> g_launches{0};
+
+int set_error(int code, const char *fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+int check_launch(const char *what) {
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return set_error(BQA_ERR_CUDA, "%s launch failed: %s", what, cudaGetErrorString(e));
+  return BQA_OK;
+}
+
+int ref_opt_n_threads(int work_size) {
+  // cuda_utils.h:15-19, same expression so the same host libm decides the power of two
+  const int pow_2 = (int)(std::log(static_cast<double>(work_size)) / std::log(2.0));
+  int v = 1 << pow_2;
+  if (v > 512) v = 512;
+  if (v < 1) v = 1;
+  return v;
+}
+
+// dispatchers implemented in the kernel translation units
+int fps_dispatch(int b, int n, int m, const float *xyz, int *idxs, float *new_xyz, float *scratch,
+                 cudaStream_t stream);
+long long fps_scratch_bytes(int b, int n);
+int ball_query_dispatch(int b, int n, int m, float radius, int nsample, const float *new_xyz,
+                        const float *xyz, int *idx, cudaStream_t stream);
+int gather_rows_dispatch(int b, int c, int n, long long e_total, const float *points, const int *idx,
+                         float *out, cudaStream_t stream);
+int scatter_add_rows_dispatch(int b, int c, int n, long long e_total, const float *grad_out,
+                              const int *idx, float *grad_points, cudaStream_t stream);
+int transpose_cn_dispatch(int b, int c, int n, const float *in, float *out, cudaStream_t stream);
+int three_nn_dispatch(int b, int n, int m, const float *unknown, const float *known, float *dist2,
+                      int *idx, cudaStream_t stream);
+int three_interpolate_dispatch(int b, int c, int m, int n, const float *points, const int *idx,
+                               const float *weight, float *out, cudaStream_t stream);
+int three_interpolate_grad_dispatch(int b, int c, int n, int m, const float *grad_out, const int *idx,
+                                    const float *weight, float *grad_points, cudaStream_t stream);
+
+}  // namespace bqa
+
+using namespace bqa;
+
+#define NONNEG(x) BQA_REQUIRE((x) >= 0, "%s: %s must be >= 0 (got %d)", __func__, #x, (int)(x))
+#define PTR(p) BQA_REQUIRE((p) != nullptr, "%s: %s is NULL", __func__, #p)
+
+extern "C" {
+
+int bqa_abi_version(void) { return BQA_ABI_VERSION; }
+const char *bqa_last_error(void) { return g_err; }
+long long bqa_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+
+long long bqa_fps_scratch_bytes(int b, int n) { return fps_scratch_bytes(b, n); }
+
+int bqa_furthest_point_sampling(int b, int n, int m, const float *xyz, int *idxs, float *new_xyz,
+                                float *scratch, void *stream) {
+  NONNEG(b); NONNEG(n); NONNEG(m);
+  if (b == 0 || m == 0) return BQA_OK;
+  BQA_REQUIRE(n > 0, "%s: n must be > 0 when m > 0", __func__);
+  PTR(xyz); PTR(idxs);
+  return fps_dispatch(b, n, m, xyz, idxs, new_xyz, scratch, (cudaStream_t)stream);
+}
+
+int bqa_gather_points(int b, int c, int n, int m, const float *points, const int *idx, float *out,
+                      void *stream) {
+  NONNEG(b); NONNEG(c); NONNEG(n); NONNEG(m);
+  if ((long long)b * c * m == 0) return BQA_OK;
+  PTR(points); PTR(idx); PTR(out);
+  return gather_rows_dispatch(b, c, n, m, points, idx, out, (cudaStream_t)stream);
+}
+
+int bqa_gather_points_grad(int b, int c, int n, int m, const float *grad_out, const int *idx,
+                           float *grad_points, void *stream) {
+  NONNEG(b); NONNEG(c); NONNEG(n); NONNEG(m);
+  if ((long long)b * c * n == 0) return BQA_OK;
+  PTR(grad_points);
+  if (m > 0) { PTR(grad_out); PTR(idx); }
+  return scatter_add_rows_dispatch(b, c, n, m, grad_out, idx, grad_points, (cudaStream_t)stream);
+}
+
+int bqa_ball_query(int b, int n, int m, float radius, int nsample, const float *new_xyz,
+                   const float *xyz, int *idx, void *stream) {
+  NONNEG(b); NONNEG(n); NONNEG(m); NONNEG(nsample);
+  if ((long long)b * m * nsample == 0) return BQA_OK;
+  PTR(new_xyz); PTR(idx);
+  if (n > 0) PTR(xyz);
+  return ball_query_dispatch(b, n, m, radius, nsample, new_xyz, xyz, idx, (cudaStream_t)stream);
+}
+
+int bqa_group_points(int b, int c, int n, int npoints, int nsample, const float *points,
+                     const int *idx, float *out, void *stream) {
+  NONNEG(b); NONNEG(c); NONNEG(n); NONNEG(npoints); NONNEG(nsample);
+  const long long e = (long long)npoints * nsample;
+  if ((long long)b * c * e == 0) return BQA_OK;
+  PTR(points); PTR(idx); PTR(out);
+  return gather_rows_dispatch(b, c, n, e, points, idx, out, (cudaStream_t)stream);
+}
+
+int bqa_group_points_grad(int b, int c, int n, int npoints, int nsample, const float *grad_out,
+                          const int *idx, float *grad_points, void *stream) {
+  NONNEG(b); NONNEG(c); NONNEG(n); NONNEG(npoints); NONNEG(nsample);
+  if ((long long)b * c * n == 0) return BQA_OK;
+  PTR(grad_points);
+  const long long e = (long long)npoints * nsample;
+  if (e > 0) { PTR(grad_out); PTR(idx); }
+  return scatter_add_rows_dispatch(b, c, n, e, grad_out, idx, grad_points, (cudaStream_t)stream);
+}
+
+int bqa_three_nn(int b, int n, int m, const float *unknown, const float *known, float *dist2,
+                 int *idx, void *stream) {
+  NONNEG(b); NONNEG(n); NONNEG(m);
+  if ((long long)b * n == 0) return BQA_OK;
+  PTR(unknown); PTR(dist2); PTR(idx);
+  if (m > 0) PTR(known);
+  return three_nn_dispatch(b, n, m, unknown, known, dist2, idx, (cudaStream_t)stream);
+}
+
+int bqa_three_interpolate(int b, int c, int m, int n, const float *points, const int *idx,
+                          const float *weight, float *out, void *stream) {
+  NONNEG(b); NONNEG(c); NONNEG(m); NONNEG(n);
+  if ((long long)b * c * n == 0) return BQA_OK;
+  PTR(points); PTR(idx); PTR(weight); PTR(out);
+  return three_interpolate_dispatch(b, c, m, n, points, idx, weight, out, (cudaStream_t)stream);
+}
+
+int bqa_three_interpolate_grad(int b, int c, int n, int m, const float *grad_out, const int *idx,
+                               const float *weight, float *grad_points, void *stream) {
+  NONNEG(b); NONNEG(c); NONNEG(m); NONNEG(n);
+  if ((long long)b * c * m == 0) return BQA_OK;
+  PTR(grad_points);
+  if (n > 0) { PTR(grad_out); PTR(idx); PTR(weight); }
+  return three_interpolate_grad_dispatch(b, c, n, m, grad_out, idx, weight, grad_points,
+                                         (cudaStream_t)stream);
+}
+
+int bqa_transpose_to_point_major(int b, int c, int n, const float *in, float *out, void *stream) {
+  NONNEG(b); NONNEG(c); NONNEG(n);
+  if ((long long)b * c * n == 0) return BQA_OK;
+  PTR(in); PTR(out);
+  return transpose_cn_dispatch(b, c, n, in, out, (cudaStream_t)stream);
+}
+
+}  // extern "C"

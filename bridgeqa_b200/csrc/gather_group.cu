@@ -1,0 +1,112 @@
+// gather_group.cu -- index gathers and their scatter-add gradients for sm_100a.
+//
+// Replaces /root/reference/lib/pointnet2/_ext_src/src/sampling_gpu.cu:8-57
+// (gather_points[_grad]) and src/group_points_gpu.cu:8-75 (group_points[_grad]).
+// The reference launches grid = B (group) or (B, C) (gather) -- 16 CTAs on a 148-SM
+// part; here the (row, channel, scene) space is tiled so the grid covers the chip,
+// the index row is read once per CTA and reused for kChan channels, and all index /
+// output traffic is coalesced (only the gathered reads are scattered, and they hit L2:
+// one channel row of a 40k-point scene is 160 KB).
+//
+// These are the un-fused parity ops (bit-exact copies).  The inference path uses the
+// fused SA kernel instead and never materialises the grouped tensor.
+#include "common.cuh"
+
+namespace bqa {
+namespace {
+
+constexpr int kThreads = 256;
+constexpr int kChan = 8;  // channels handled per CTA for one slab of indices
+
+// out[(s*c + l)*e_total + e] = points[(s*c + l)*n + idx[s*e_total + e]]
+// covers gather (e_total = m) and group (e_total = npoints*nsample).
+__global__ void __launch_bounds__(kThreads)
+gather_rows_kernel(int c, int n, int e_total, const float *__restrict__ points,
+                   const int *__restrict__ idx, float *__restrict__ out) {
+  const int scene = blockIdx.z;
+  const int l0 = blockIdx.y * kChan;
+  const int e = blockIdx.x * kThreads + threadIdx.x;
+  if (e >= e_total) return;
+  const int a = idx[(size_t)scene * e_total + e];
+  const int lend = min(l0 + kChan, c);
+  for (int l = l0; l < lend; ++l) {
+    const size_t row = (size_t)scene * c + l;
+    out[row * e_total + e] = __ldg(points + row * n + a);
+  }
+}
+
+// grad_points[(s*c + l)*n + idx[s*e_total + e]] += grad_out[(s*c + l)*e_total + e]
+__global__ void __launch_bounds__(kThreads)
+scatter_add_rows_kernel(int c, int n, int e_total, const float *__restrict__ grad_out,
+                        const int *__restrict__ idx, float *__restrict__ grad_points) {
+  const int scene = blockIdx.z;
+  const int l0 = blockIdx.y * kChan;
+  const int e = blockIdx.x * kThreads + threadIdx.x;
+  if (e >= e_total) return;
+  const int a = idx[(size_t)scene * e_total + e];
+  const int lend = min(l0 + kChan, c);
+  for (int l = l0; l < lend; ++l) {
+    const size_t row = (size_t)scene * c + l;
+    atomicAdd(grad_points + row * n + a, grad_out[row * e_total + e]);
+  }
+}
+
+// (b,c,n) -> (b,n,c) through a 32x32 shared tile (both sides coalesced)
+__global__ void __launch_bounds__(256)
+transpose_cn_kernel(int c, int n, const float *__restrict__ in, float *__restrict__ out) {
+  __shared__ float tile[32][33];
+  const int scene = blockIdx.z;
+  const int n0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
+  const float *src = in + (size_t)scene * c * n;
+  float *dst = out + (size_t)scene * c * n;
+  for (int r = ty; r < 32; r += 8) {
+    const int cc = c0 + r, nn = n0 + tx;
+    tile[r][tx] = (cc < c && nn < n) ? src[(size_t)cc * n + nn] : 0.f;
+  }
+  __syncthreads();
+  for (int r = ty; r < 32; r += 8) {
+    const int nn = n0 + r, cc = c0 + tx;
+    if (nn < n && cc < c) dst[(size_t)nn * c + cc] = tile[tx][r];
+  }
+}
+
+int check_grid(long long e_total, int c, int b) {
+  if (ceil_div_ll(e_total, kThreads) > 2147483647ll || ceil_div(c, kChan) > 65535 || b > 65535)
+    return set_error(BQA_ERR_UNSUPPORTED, "gather/group: grid too large (e=%lld c=%d b=%d)", e_total, c, b);
+  return BQA_OK;
+}
+
+}  // namespace
+
+int gather_rows_dispatch(int b, int c, int n, long long e_total, const float *points,
+                         const int *idx, float *out, cudaStream_t stream) {
+  if (b == 0 || c == 0 || e_total == 0) return BQA_OK;
+  if (int rc = check_grid(e_total, c, b)) return rc;
+  dim3 grid((unsigned)ceil_div_ll(e_total, kThreads), (unsigned)ceil_div(c, kChan), (unsigned)b);
+  gather_rows_kernel<<<grid, kThreads, 0, stream>>>(c, n, (int)e_total, points, idx, out);
+  count_launch();
+  return check_launch("gather_rows_kernel");
+}
+
+int scatter_add_rows_dispatch(int b, int c, int n, long long e_total, const float *grad_out,
+                              const int *idx, float *grad_points, cudaStream_t stream) {
+  // torch::zeros in the reference wrappers (sampling.cpp:51-53, group_points.cpp:49-51)
+  BQA_CUDA(cudaMemsetAsync(grad_points, 0, sizeof(float) * (size_t)b * c * n, stream));
+  if (b == 0 || c == 0 || e_total == 0) return BQA_OK;
+  if (int rc = check_grid(e_total, c, b)) return rc;
+  dim3 grid((unsigned)ceil_div_ll(e_total, kThreads), (unsigned)ceil_div(c, kChan), (unsigned)b);
+  scatter_add_rows_kernel<<<grid, kThreads, 0, stream>>>(c, n, (int)e_total, grad_out, idx, grad_points);
+  count_launch();
+  return check_launch("scatter_add_rows_kernel");
+}
+
+int transpose_cn_dispatch(int b, int c, int n, const float *in, float *out, cudaStream_t stream) {
+  if (b == 0 || c == 0 || n == 0) return BQA_OK;
+  dim3 grid((unsigned)ceil_div(n, 32), (unsigned)ceil_div(c, 32), (unsigned)b);
+  transpose_cn_kernel<<<grid, 256, 0, stream>>>(c, n, in, out);
+  count_launch();
+  return check_launch("transpose_cn_kernel");
+}
+
+}  // namespace bqa

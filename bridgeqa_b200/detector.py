@@ -1,0 +1,245 @@
+"""VoteNet detector front-end built on the B200 point-cloud operators: host mirror of the
+three reference model files that sit directly on the hot path,
+
+    Pointnet2Backbone   /root/reference/models/backbone_module.py:11-131
+    VotingModule        /root/reference/models/voting_module.py:11-60
+    ProposalModule      /root/reference/models/proposal_module.py:20-151
+
+with identical constructor arguments, data_dict keys and state_dict keys, so a BridgeQA /
+VoteNet checkpoint's `detection_backbone.*`, `voting_net.*` and `proposal_net.*` entries
+load with strict=True.  (The reference files themselves also run unchanged on top of
+`bridgeqa_b200.compat`; see INTEGRATION.md.  These classes exist because the reference
+tree does not travel to the benchmark machine.)
+
+`detect()` strings them together the way ScanQA.forward does
+(/root/reference/models/qa_module.py:438-459).
+"""
+import math
+
+import numpy as np
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from .pointnet2_modules import PointnetFPModule, PointnetSAModuleVotes
+
+
+class Pointnet2Backbone(nn.Module):
+    """PointNet++ single-scale-grouping backbone: 4 set-abstraction + 2 feature-propagation
+    layers.  Input data_dict["point_clouds"] is (B, N, 3 + input_feature_dim)."""
+
+    # (npoint, radius, nsample, in_width_units, hidden_units, out_units) in units of `width`
+    _SA = (
+        (2048, 0.2, 64, None, 64, 128),
+        (1024, 0.4, 32, 128, 128, 256),
+        (512, 0.8, 16, 256, 128, 256),
+        (256, 1.2, 16, 256, 128, 256),
+    )
+
+    def __init__(self, input_feature_dim=0, width=1, depth=2, seed_feat_dim=256):
+        super().__init__()
+        self.input_feature_dim = input_feature_dim
+        for i, (npoint, radius, nsample, cin, hid, cout) in enumerate(self._SA, start=1):
+            first = input_feature_dim if cin is None else cin * width
+            spec = [first] + [hid * width] * depth + [cout * width]
+            setattr(self, "sa%d" % i, PointnetSAModuleVotes(
+                npoint=npoint, radius=radius, nsample=nsample, mlp=spec, use_xyz=True,
+                normalize_xyz=True))
+        c = 256 * width
+        self.fp1 = PointnetFPModule(mlp=[c + c, c, c])
+        self.fp2 = PointnetFPModule(mlp=[c + c, c, seed_feat_dim])
+
+    @staticmethod
+    def _break_up_pc(pc):
+        xyz = pc[..., :3].contiguous()
+        features = pc[..., 3:].transpose(1, 2).contiguous() if pc.size(-1) > 3 else None
+        return xyz, features
+
+    def forward(self, data_dict):
+        xyz, features = self._break_up_pc(data_dict["point_clouds"])
+
+        xyz, features, inds = self.sa1(xyz, features)
+        data_dict["sa1_inds"], data_dict["sa1_xyz"], data_dict["sa1_features"] = inds, xyz, features
+        xyz, features, inds = self.sa2(xyz, features)
+        data_dict["sa2_inds"], data_dict["sa2_xyz"], data_dict["sa2_features"] = inds, xyz, features
+        xyz, features, inds = self.sa3(xyz, features)
+        data_dict["sa3_xyz"], data_dict["sa3_features"] = xyz, features
+        xyz, features, inds = self.sa4(xyz, features)
+        data_dict["sa4_xyz"], data_dict["sa4_features"] = xyz, features
+
+        features = self.fp1(data_dict["sa3_xyz"], data_dict["sa4_xyz"],
+                            data_dict["sa3_features"], data_dict["sa4_features"])
+        features = self.fp2(data_dict["sa2_xyz"], data_dict["sa3_xyz"],
+                            data_dict["sa2_features"], features)
+        data_dict["fp2_features"] = features
+        data_dict["fp2_xyz"] = data_dict["sa2_xyz"]
+        num_seed = data_dict["fp2_xyz"].shape[1]
+        # seeds index the ORIGINAL cloud: the first num_seed SA1 samples (backbone_module.py:130)
+        data_dict["fp2_inds"] = data_dict["sa1_inds"][:, 0:num_seed]
+        return data_dict
+
+
+class VotingModule(nn.Module):
+    """Seeds -> votes: 3 pointwise convs; output = seed + predicted (xyz offset, feature residual)."""
+
+    def __init__(self, vote_factor, seed_feature_dim):
+        super().__init__()
+        self.vote_factor = vote_factor
+        self.in_dim = seed_feature_dim
+        self.out_dim = self.in_dim
+        self.conv1 = nn.Conv1d(self.in_dim, self.in_dim, 1)
+        self.conv2 = nn.Conv1d(self.in_dim, self.in_dim, 1)
+        self.conv3 = nn.Conv1d(self.in_dim, (3 + self.out_dim) * self.vote_factor, 1)
+        self.bn1 = nn.BatchNorm1d(self.in_dim)
+        self.bn2 = nn.BatchNorm1d(self.in_dim)
+
+    def forward(self, seed_xyz, seed_features):
+        b, num_seed = seed_xyz.shape[0], seed_xyz.shape[1]
+        vf, d = self.vote_factor, self.out_dim
+        net = F.relu(self.bn1(self.conv1(seed_features)))
+        net = F.relu(self.bn2(self.conv2(net)))
+        net = self.conv3(net)                                   # (B, (3+d)*vf, num_seed)
+        net = net.transpose(2, 1).reshape(b, num_seed, vf, 3 + d)
+        vote_xyz = (seed_xyz.unsqueeze(2) + net[..., 0:3]).reshape(b, num_seed * vf, 3)
+        vote_features = seed_features.transpose(2, 1).unsqueeze(2) + net[..., 3:]
+        vote_features = vote_features.reshape(b, num_seed * vf, d).transpose(2, 1).contiguous()
+        return vote_xyz.contiguous(), vote_features
+
+
+class DatasetConfig(object):
+    """Stand-in for `data.scannet.model_util_scannet.ScannetDatasetConfig`, which the
+    reference imports (models/proposal_module.py:11) from an un-vendored data tree (dangling
+    symlink in /root/reference).  ScanNet boxes are axis-aligned: one heading bin whose angle
+    is always 0; 18 classes = 18 size clusters.  mean_size_arr is data (a .npz in the
+    original); here it defaults to ones and can be replaced."""
+
+    def __init__(self, num_class=18, num_heading_bin=1, num_size_cluster=18, mean_size_arr=None):
+        self.num_class = num_class
+        self.num_heading_bin = num_heading_bin
+        self.num_size_cluster = num_size_cluster
+        self.mean_size_arr = (np.ones((num_size_cluster, 3), dtype=np.float32)
+                              if mean_size_arr is None else np.asarray(mean_size_arr, dtype=np.float32))
+
+    def class2angle(self, pred_cls, residual, to_label_format=True):
+        return 0
+
+    def class2size(self, pred_cls, residual):
+        return self.mean_size_arr[pred_cls] + residual
+
+
+def box_corners(box_size, heading_angle, center):
+    """Torch / on-device version of utils/box_util.py:302-325 (get_3d_box_batch):
+    box_size (...,3), heading (...), center (...,3) -> (...,8,3)."""
+    l, w, h = box_size[..., 0:1] / 2, box_size[..., 1:2] / 2, box_size[..., 2:3] / 2
+    cx = torch.cat((l, l, -l, -l, l, l, -l, -l), -1)
+    cy = torch.cat((w, -w, -w, w, w, -w, -w, w), -1)
+    cz = torch.cat((h, h, h, h, -h, -h, -h, -h), -1)
+    c, s = torch.cos(heading_angle).unsqueeze(-1), torch.sin(heading_angle).unsqueeze(-1)
+    # corners @ R^T with R = roty(t) = [[c,0,s],[0,1,0],[-s,0,c]]
+    x = cx * c + cz * s
+    z = -cx * s + cz * c
+    return torch.stack((x, cy, z), -1) + center.unsqueeze(-2)
+
+
+class ProposalModule(nn.Module):
+    """Vote aggregation (an SA layer over the votes) + proposal head + score decoding."""
+
+    def __init__(self, num_class, num_heading_bin, num_size_cluster, mean_size_arr, num_proposal,
+                 sampling, seed_feat_dim=256, proposal_size=128, radius=0.3, nsample=16):
+        super().__init__()
+        self.num_class = num_class
+        self.num_heading_bin = num_heading_bin
+        self.num_size_cluster = num_size_cluster
+        self.mean_size_arr = mean_size_arr
+        self.num_proposal = num_proposal
+        self.sampling = sampling
+        self.seed_feat_dim = seed_feat_dim
+        self.votenet_hidden_size = proposal_size
+        self.vote_aggregation = PointnetSAModuleVotes(
+            npoint=num_proposal, radius=radius, nsample=nsample,
+            mlp=[seed_feat_dim, proposal_size, proposal_size, proposal_size],
+            use_xyz=True, normalize_xyz=True)
+        out_ch = 2 + 3 + num_heading_bin * 2 + num_size_cluster * 4 + num_class
+        self.proposal = nn.Sequential(
+            nn.Conv1d(proposal_size, proposal_size, 1, bias=False),
+            nn.BatchNorm1d(proposal_size),
+            nn.ReLU(),
+            nn.Conv1d(proposal_size, proposal_size, 1, bias=False),
+            nn.BatchNorm1d(proposal_size),
+            nn.ReLU(),
+            nn.Conv1d(proposal_size, out_ch, 1))
+        self.register_buffer("_mean_size", torch.as_tensor(np.asarray(mean_size_arr, dtype=np.float32)),
+                             persistent=False)
+
+    def forward(self, xyz, features, data_dict):
+        xyz, features, fps_inds = self.vote_aggregation(xyz, features)
+        data_dict["aggregated_vote_xyz"] = xyz
+        data_dict["aggregated_vote_features"] = features.permute(0, 2, 1).contiguous()
+        data_dict["aggregated_vote_inds"] = fps_inds
+        net = self.proposal(features)                         # (B, 97, num_proposal)
+        return self.decode_scores(net, data_dict)
+
+    def decode_scores(self, net, data_dict):
+        nh, ns = self.num_heading_bin, self.num_size_cluster
+        t = net.transpose(2, 1).contiguous()                  # (B, K, 97)
+        b, k = t.shape[0], t.shape[1]
+        o = 5 + 2 * nh
+        data_dict["objectness_scores"] = t[:, :, 0:2]
+        data_dict["center"] = data_dict["aggregated_vote_xyz"] + t[:, :, 2:5]
+        data_dict["heading_scores"] = t[:, :, 5:5 + nh]
+        data_dict["heading_residuals_normalized"] = t[:, :, 5 + nh:o]
+        data_dict["heading_residuals"] = data_dict["heading_residuals_normalized"] * (math.pi / nh)
+        data_dict["size_scores"] = t[:, :, o:o + ns]
+        srn = t[:, :, o + ns:o + 4 * ns].view(b, k, ns, 3)
+        data_dict["size_residuals_normalized"] = srn
+        data_dict["size_residuals"] = srn * self._mean_size.to(srn.device)[None, None]
+        data_dict["sem_cls_scores"] = t[:, :, o + 4 * ns:]
+        data_dict["bbox_corner"] = self.decode_pred_box(data_dict)
+        data_dict["bbox_feature"] = data_dict["aggregated_vote_features"]
+        data_dict["bbox_mask"] = data_dict["objectness_scores"].argmax(-1)
+        data_dict["bbox_sems"] = data_dict["sem_cls_scores"].argmax(-1)
+        return data_dict
+
+    def decode_pred_box(self, data_dict):
+        """Box corners (B, K, 8, 3) on the device.  The reference does this through
+        .cpu().numpy() + param2obb_batch + get_3d_box_batch + .cuda()
+        (proposal_module.py:87-108), a host sync inside the forward; with ScanNet's single
+        zero-angle heading bin the result is center +- size/2, computed here in torch."""
+        size_cls = torch.argmax(data_dict["size_scores"], -1)                       # (B,K)
+        res = torch.gather(data_dict["size_residuals"], 2,
+                           size_cls[..., None, None].expand(-1, -1, 1, 3)).squeeze(2)
+        box_size = self._mean_size.to(res.device)[size_cls] + res
+        heading = torch.zeros_like(box_size[..., 0])      # class2angle == 0 for ScanNet
+        return box_corners(box_size, heading, data_dict["center"])
+
+
+class VoteNetDetector(nn.Module):
+    """backbone -> voting -> L2-normalise vote features -> proposal, i.e. the detection
+    branch of ScanQA.forward (models/qa_module.py:438-459) with the reference's default
+    hyper-parameters (scripts/train.py:71-86)."""
+
+    def __init__(self, input_feature_dim, config=None, num_proposal=256, vote_factor=1,
+                 sampling="vote_fps", seed_feat_dim=256, proposal_size=128, pointnet_width=1,
+                 pointnet_depth=2, vote_radius=0.3, vote_nsample=16):
+        super().__init__()
+        cfg = config or DatasetConfig()
+        self.detection_backbone = Pointnet2Backbone(
+            input_feature_dim=input_feature_dim, width=pointnet_width, depth=pointnet_depth,
+            seed_feat_dim=seed_feat_dim)
+        self.voting_net = VotingModule(vote_factor, seed_feat_dim)
+        self.proposal_net = ProposalModule(
+            cfg.num_class, cfg.num_heading_bin, cfg.num_size_cluster, cfg.mean_size_arr,
+            num_proposal, sampling, seed_feat_dim=seed_feat_dim, proposal_size=proposal_size,
+            radius=vote_radius, nsample=vote_nsample)
+
+    def forward(self, data_dict):
+        data_dict = self.detection_backbone(data_dict)
+        xyz, features = data_dict["fp2_xyz"], data_dict["fp2_features"]
+        data_dict["seed_inds"] = data_dict["fp2_inds"]
+        data_dict["seed_xyz"] = xyz
+        data_dict["seed_features"] = features
+        xyz, features = self.voting_net(xyz, features)
+        features = features.div(torch.norm(features, p=2, dim=1).unsqueeze(1))
+        data_dict["vote_xyz"] = xyz
+        data_dict["vote_features"] = features
+        return self.proposal_net(xyz, features, data_dict)

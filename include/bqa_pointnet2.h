@@ -1,0 +1,108 @@
+/*
+ * bqa_pointnet2.h -- C ABI of libbqa_pointnet2.so, the B200 (sm_100a) replacement for
+ * BridgeQA's `pointnet2._ext` pybind module.
+ *
+ * Every entry point takes raw DEVICE pointers, int sizes and a `cudaStream_t` passed
+ * as `void*`; it enqueues work on that stream and returns immediately (no host sync,
+ * no allocation).  Return value: 0 = ok, nonzero = BQA_ERR_* (message via
+ * bqa_last_error(), thread-local).  The library never calls exit(): the reference's
+ * CUDA_CHECK_ERRORS() (lib/pointnet2/_ext_src/include/cuda_utils.h:30-39) does.
+ *
+ * "replaces" cites the reference interface the entry stands in for, relative to
+ * /root/reference/lib/pointnet2/_ext_src/.  Tensor layouts and index dtype (int32)
+ * are the reference's.  Output buffers need NOT be pre-zeroed (the reference relies
+ * on torch::zeros for ball_query rows and every *_grad; here the library does it).
+ */
+#ifndef BQA_POINTNET2_H_
+#define BQA_POINTNET2_H_
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BQA_OK 0
+#define BQA_ERR_INVALID_ARG 1
+#define BQA_ERR_CUDA 2
+#define BQA_ERR_UNSUPPORTED 3
+
+#define BQA_ABI_VERSION 1
+
+#if defined(__GNUC__)
+#define BQA_API __attribute__((visibility("default")))
+#else
+#define BQA_API
+#endif
+
+/* ---- library ---------------------------------------------------------------- */
+BQA_API int bqa_abi_version(void);
+/* last error message of the calling thread ("" if none) */
+BQA_API const char *bqa_last_error(void);
+/* number of kernels this library has launched since load (all threads) */
+BQA_API long long bqa_launch_count(void);
+
+/* ---- furthest point sampling -------------------------------------------------
+ * replaces: furthest_point_sampling(points (B,N,3), nsamples) -> (B,nsamples) int32
+ *           src/sampling.cpp:66-87, kernel src/sampling_gpu.cu:69-173.
+ * xyz (b,n,3) f32, idxs (b,m) i32.  Bit-exact index contract incl. the 1e-3 norm
+ * skip and the 512-slot tree tie-break.  The reference's (b,n) `temp` scratch is not
+ * needed: running min-distances live in registers of a thread-block cluster.
+ * new_xyz (b,m,3) f32 may be NULL; when given, the sampled coordinates are written
+ * too (fused gather_points of src/sampling_gpu.cu:8-20 on xyz).
+ * scratch: NULL unless bqa_fps_scratch_bytes(b, n) > 0 (scenes beyond 131072 points,
+ * which fall back to a global-memory variant needing the reference's (b,n) temp).  */
+BQA_API long long bqa_fps_scratch_bytes(int b, int n);
+BQA_API int bqa_furthest_point_sampling(int b, int n, int m, const float *xyz, int *idxs,
+                                float *new_xyz, float *scratch, void *stream);
+
+/* ---- gather -------------------------------------------------------------------
+ * replaces: gather_points / gather_points_grad, src/sampling.cpp:15-65,
+ *           kernels src/sampling_gpu.cu:8-57.
+ * points (b,c,n), idx (b,m) -> out (b,c,m);  grad_out (b,c,m) -> grad_points (b,c,n) */
+BQA_API int bqa_gather_points(int b, int c, int n, int m, const float *points, const int *idx,
+                      float *out, void *stream);
+BQA_API int bqa_gather_points_grad(int b, int c, int n, int m, const float *grad_out,
+                           const int *idx, float *grad_points, void *stream);
+
+/* ---- ball query ---------------------------------------------------------------
+ * replaces: ball_query(new_xyz (B,M,3), xyz (B,N,3), radius, nsample) -> (B,M,nsample)
+ *           src/ball_query.cpp:8-32, kernel src/ball_query_gpu.cu:9-54.
+ * First `nsample` indices k (ascending) with d2 < radius*radius, first hit back-fills
+ * the row, empty ball -> zeros.  */
+BQA_API int bqa_ball_query(int b, int n, int m, float radius, int nsample, const float *new_xyz,
+                   const float *xyz, int *idx, void *stream);
+
+/* ---- grouping -----------------------------------------------------------------
+ * replaces: group_points / group_points_grad, src/group_points.cpp:12-62,
+ *           kernels src/group_points_gpu.cu:8-75.
+ * points (b,c,n), idx (b,npoints,nsample) -> out (b,c,npoints,nsample) */
+BQA_API int bqa_group_points(int b, int c, int n, int npoints, int nsample, const float *points,
+                     const int *idx, float *out, void *stream);
+BQA_API int bqa_group_points_grad(int b, int c, int n, int npoints, int nsample,
+                          const float *grad_out, const int *idx, float *grad_points,
+                          void *stream);
+
+/* ---- three_nn / three_interpolate --------------------------------------------
+ * replaces: three_nn, three_interpolate, three_interpolate_grad,
+ *           src/interpolate.cpp:14-99, kernels src/interpolate_gpu.cu:9-154.
+ * unknown (b,n,3), known (b,m,3) -> dist2 (b,n,3) f32 (SQUARED), idx (b,n,3) i32
+ * points (b,c,m), idx (b,n,3), weight (b,n,3) -> out (b,c,n) */
+BQA_API int bqa_three_nn(int b, int n, int m, const float *unknown, const float *known,
+                 float *dist2, int *idx, void *stream);
+BQA_API int bqa_three_interpolate(int b, int c, int m, int n, const float *points, const int *idx,
+                          const float *weight, float *out, void *stream);
+BQA_API int bqa_three_interpolate_grad(int b, int c, int n, int m, const float *grad_out,
+                               const int *idx, const float *weight, float *grad_points,
+                               void *stream);
+
+/* ---- layout helper -------------------------------------------------------------
+ * (b,c,n) channel-major -> (b,n,c) point-major, the layout the fused SA kernel gathers
+ * from (one contiguous row per neighbour).  Replaces nothing in the reference; it is
+ * the inverse of the transpose in Pointnet2Backbone._break_up_pc
+ * (models/backbone_module.py:74-78). */
+BQA_API int bqa_transpose_to_point_major(int b, int c, int n, const float *in, float *out,
+                                 void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BQA_POINTNET2_H_ */

@@ -1,0 +1,274 @@
+/*
+ * pointnet2_oracle.c -- CPU restatement of the reference's nine pointnet2 CUDA
+ * kernels (/root/reference/lib/pointnet2/_ext_src/src/*_gpu.cu).
+ *
+ * TEST INFRASTRUCTURE ONLY.  This file is the parity checker and the reported
+ * CPU baseline.  Only tests/, __graft_entry__.smoke() and bench.py's
+ * cpu_baseline / --impl reference legs may load it.  The product
+ * (bridgeqa_b200/) never links, imports or calls anything in oracle/.
+ *
+ * Parity status: PINNED.  The reference has no golden vectors for this path
+ * (its only test is a gradcheck, pointnet2_test.py:18-30), so the pin is the
+ * reference's own extension built unmodified into oracle/_ref (build_ref.py)
+ * and executed on the B200 box: tests/test_ref_ext_gpu.py compares this file
+ * with it bit-for-bit, and tests/golden/ref_ext_*.npz are outputs of that
+ * extension (generator: tests/golden/make_golden_gpu.py) that the CPU-only
+ * suite replays against this file.
+ *
+ * Arithmetic rules that make the results bit-identical to the nvcc build of
+ * the reference (checked against its sm_100a SASS):
+ *   - nvcc contracts  a*a + b*b + c*c  to  fma(c,c, fma(b,b, a*a))  in fp32;
+ *     this file is compiled with -ffp-contract=off and spells each fmaf().
+ *   - `mag <= 1e-3` compares (double)mag with the double literal.
+ *   - three_nn keeps its running bests in double, starting at 1e40.
+ *   - FPS reduces 512 per-thread partials with a 9-step pairwise tree in which
+ *     ties keep the lower slot.
+ */
+#include <math.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+
+#if defined(__x86_64__) && defined(__GNUC__) && !defined(BQA_NO_CLONES)
+#define HOT __attribute__((target_clones("avx2,fma", "default")))
+#else
+#define HOT
+#endif
+
+/* cuda_utils.h:15-19  opt_n_threads */
+int bqa_oracle_opt_n_threads(int work_size) {
+  const int pow_2 = (int)(log((double)work_size) / log(2.0));
+  int v = 1 << pow_2;
+  if (v > 512) v = 512;
+  if (v < 1) v = 1;
+  return v;
+}
+
+static inline float sqdist(float ax, float ay, float az, float bx, float by, float bz) {
+  /* (a-b)*(a-b) + ... as nvcc contracts it */
+  const float dx = ax - bx, dy = ay - by, dz = az - bz;
+  return fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+}
+
+/* ------------------------------------------------------------------ FPS --- */
+/* sampling_gpu.cu:69-173 (kernel) + sampling.cpp:66-87 (temp = 1e10, out = 0).
+ * One "thread" t of the reference owns k = t, t+bs, t+2bs ...; this loop walks
+ * k ascending and updates partial[k % bs], which visits every thread's points
+ * in the same order. */
+HOT static void fps_one_scene(int n, int m, const float *xyz, float *temp, int *idxs,
+                              int bs, float *best, int *besti) {
+  if (m <= 0) return;
+  int old = 0;
+  idxs[0] = old;                                        /* :85-86 */
+  for (int j = 1; j < m; j++) {                          /* :89 */
+    const float x1 = xyz[old * 3 + 0], y1 = xyz[old * 3 + 1], z1 = xyz[old * 3 + 2];
+    for (int t = 0; t < bs; t++) { best[t] = -1.0f; besti[t] = 0; }   /* :90-91 */
+    for (int base = 0; base < n; base += bs) {
+      const int lim = (n - base) < bs ? (n - base) : bs;
+      for (int t = 0; t < lim; t++) {
+        const int k = base + t;
+        const float x2 = xyz[k * 3 + 0], y2 = xyz[k * 3 + 1], z2 = xyz[k * 3 + 2];
+        const float mag = fmaf(z2, z2, fmaf(y2, y2, x2 * x2));        /* :100 */
+        if ((double)mag <= 1e-3) continue;                            /* :101 */
+        const float dx = x2 - x1, dy = y2 - y1, dz = z2 - z1;          /* :103-104 */
+        const float d = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+        const float d2 = fminf(d, temp[k]);                           /* :106 */
+        temp[k] = d2;                                                 /* :107 */
+        if (d2 > best[t]) { besti[t] = k; best[t] = d2; }             /* :108-109 */
+      }
+    }
+    for (int s = bs >> 1; s >= 1; s >>= 1) {            /* :115-168, __update :59-65 */
+      for (int t = 0; t < s; t++) {
+        const float v1 = best[t], v2 = best[t + s];
+        const int i1 = besti[t], i2 = besti[t + s];
+        best[t] = fmaxf(v1, v2);
+        besti[t] = v2 > v1 ? i2 : i1;
+      }
+    }
+    old = besti[0];                                     /* :170 */
+    idxs[j] = old;                                      /* :171 */
+  }
+}
+
+/* xyz (b,n,3) f32 -> idxs (b,m) i32 */
+void bqa_oracle_furthest_point_sampling(int b, int n, int m, const float *xyz, int *idxs) {
+  const int bs = bqa_oracle_opt_n_threads(n);
+#pragma omp parallel for schedule(dynamic, 1)
+  for (int i = 0; i < b; i++) {
+    float *temp = (float *)malloc(sizeof(float) * (size_t)(n > 0 ? n : 1));
+    float *best = (float *)malloc(sizeof(float) * 512);
+    int *besti = (int *)malloc(sizeof(int) * 512);
+    for (int k = 0; k < n; k++) temp[k] = 1e10f;        /* sampling.cpp:74-76 */
+    memset(idxs + (size_t)i * m, 0, sizeof(int) * (size_t)m);
+    fps_one_scene(n, m, xyz + (size_t)i * n * 3, temp, idxs + (size_t)i * m, bs, best, besti);
+    free(temp); free(best); free(besti);
+  }
+}
+
+/* ------------------------------------------------------------- gather --- */
+/* sampling_gpu.cu:8-20: out[b,c,j] = points[b,c,idx[b,j]] */
+void bqa_oracle_gather_points(int b, int c, int n, int m, const float *points,
+                              const int *idx, float *out) {
+#pragma omp parallel for collapse(2)
+  for (int i = 0; i < b; i++)
+    for (int l = 0; l < c; l++)
+      for (int j = 0; j < m; j++) {
+        const int a = idx[(size_t)i * m + j];
+        out[((size_t)i * c + l) * m + j] = points[((size_t)i * c + l) * n + a];
+      }
+}
+
+/* sampling_gpu.cu:34-46: grad_points[b,c,idx[b,j]] += grad_out[b,c,j].
+ * The reference's atomicAdd order is unspecified; this one is j-ascending. */
+void bqa_oracle_gather_points_grad(int b, int c, int n, int m, const float *grad_out,
+                                   const int *idx, float *grad_points) {
+  memset(grad_points, 0, sizeof(float) * (size_t)b * c * n);   /* sampling.cpp:51-53 */
+#pragma omp parallel for collapse(2)
+  for (int i = 0; i < b; i++)
+    for (int l = 0; l < c; l++)
+      for (int j = 0; j < m; j++) {
+        const int a = idx[(size_t)i * m + j];
+        grad_points[((size_t)i * c + l) * n + a] += grad_out[((size_t)i * c + l) * m + j];
+      }
+}
+
+/* --------------------------------------------------------- ball query --- */
+/* ball_query_gpu.cu:9-44; idx zero-filled by ball_query.cpp:19-21.
+ * new_xyz (b,m,3), xyz (b,n,3) -> idx (b,m,nsample) */
+HOT void bqa_oracle_ball_query(int b, int n, int m, float radius, int nsample,
+                               const float *new_xyz, const float *xyz, int *idx) {
+  const float radius2 = radius * radius;                /* :21 */
+#pragma omp parallel for collapse(2) schedule(static)
+  for (int i = 0; i < b; i++) {
+    for (int j = 0; j < m; j++) {
+      const float *p = xyz + (size_t)i * n * 3;
+      const float *q = new_xyz + ((size_t)i * m + j) * 3;
+      int *row = idx + ((size_t)i * m + j) * nsample;
+      for (int l = 0; l < nsample; l++) row[l] = 0;
+      const float qx = q[0], qy = q[1], qz = q[2];
+      int cnt = 0;
+      for (int k = 0; k < n && cnt < nsample; ++k) {    /* :26 */
+        const float d2 = sqdist(qx, qy, qz, p[k * 3 + 0], p[k * 3 + 1], p[k * 3 + 2]);
+        if (d2 < radius2) {                             /* :32 */
+          if (cnt == 0)
+            for (int l = 0; l < nsample; ++l) row[l] = k;   /* :33-37 */
+          row[cnt] = k;
+          ++cnt;
+        }
+      }
+    }
+  }
+}
+
+/* -------------------------------------------------------------- group --- */
+/* group_points_gpu.cu:8-28: out[b,c,j,k] = points[b,c,idx[b,j,k]] */
+void bqa_oracle_group_points(int b, int c, int n, int npoints, int nsample,
+                             const float *points, const int *idx, float *out) {
+#pragma omp parallel for collapse(2)
+  for (int i = 0; i < b; i++)
+    for (int l = 0; l < c; l++) {
+      const float *src = points + ((size_t)i * c + l) * n;
+      const int *ix = idx + (size_t)i * npoints * nsample;
+      float *dst = out + ((size_t)i * c + l) * npoints * nsample;
+      for (size_t e = 0; e < (size_t)npoints * nsample; e++) dst[e] = src[ix[e]];
+    }
+}
+
+/* group_points_gpu.cu:43-64 (atomicAdd order unspecified; here (j,k)-ascending) */
+void bqa_oracle_group_points_grad(int b, int c, int n, int npoints, int nsample,
+                                  const float *grad_out, const int *idx, float *grad_points) {
+  memset(grad_points, 0, sizeof(float) * (size_t)b * c * n);
+#pragma omp parallel for collapse(2)
+  for (int i = 0; i < b; i++)
+    for (int l = 0; l < c; l++) {
+      float *dst = grad_points + ((size_t)i * c + l) * n;
+      const int *ix = idx + (size_t)i * npoints * nsample;
+      const float *src = grad_out + ((size_t)i * c + l) * npoints * nsample;
+      for (size_t e = 0; e < (size_t)npoints * nsample; e++) dst[ix[e]] += src[e];
+    }
+}
+
+/* ----------------------------------------------------------- three_nn --- */
+/* interpolate_gpu.cu:9-58.  unknown (b,n,3), known (b,m,3) -> dist2 (b,n,3), idx (b,n,3) */
+HOT void bqa_oracle_three_nn(int b, int n, int m, const float *unknown, const float *known,
+                             float *dist2, int *idx) {
+#pragma omp parallel for collapse(2)
+  for (int i = 0; i < b; i++)
+    for (int j = 0; j < n; j++) {
+      const float *u = unknown + ((size_t)i * n + j) * 3;
+      const float *kn = known + (size_t)i * m * 3;
+      const float ux = u[0], uy = u[1], uz = u[2];
+      double best1 = 1e40, best2 = 1e40, best3 = 1e40;  /* :27 */
+      int besti1 = 0, besti2 = 0, besti3 = 0;
+      for (int k = 0; k < m; ++k) {
+        const float d = sqdist(ux, uy, uz, kn[k * 3 + 0], kn[k * 3 + 1], kn[k * 3 + 2]);
+        if (d < best1) {
+          best3 = best2; besti3 = besti2; best2 = best1; besti2 = besti1; best1 = d; besti1 = k;
+        } else if (d < best2) {
+          best3 = best2; besti3 = besti2; best2 = d; besti2 = k;
+        } else if (d < best3) {
+          best3 = d; besti3 = k;
+        }
+      }
+      float *o = dist2 + ((size_t)i * n + j) * 3;
+      int *oi = idx + ((size_t)i * n + j) * 3;
+      o[0] = (float)best1; o[1] = (float)best2; o[2] = (float)best3;   /* :50-52 */
+      oi[0] = besti1; oi[1] = besti2; oi[2] = besti3;
+    }
+}
+
+/* -------------------------------------------------- three_interpolate --- */
+/* interpolate_gpu.cu:72-101: points (b,c,m), idx (b,n,3), weight (b,n,3) -> out (b,c,n)
+ * p1*w1 + p2*w2 + p3*w3  contracts to  fma(p3,w3, fma(p2,w2, p1*w1)). */
+HOT void bqa_oracle_three_interpolate(int b, int c, int m, int n, const float *points,
+                                      const int *idx, const float *weight, float *out) {
+#pragma omp parallel for collapse(2)
+  for (int i = 0; i < b; i++)
+    for (int l = 0; l < c; l++) {
+      const float *p = points + ((size_t)i * c + l) * m;
+      const int *ix = idx + (size_t)i * n * 3;
+      const float *w = weight + (size_t)i * n * 3;
+      float *o = out + ((size_t)i * c + l) * n;
+      for (int j = 0; j < n; j++)
+        o[j] = fmaf(p[ix[j * 3 + 2]], w[j * 3 + 2],
+                    fmaf(p[ix[j * 3 + 1]], w[j * 3 + 1], p[ix[j * 3 + 0]] * w[j * 3 + 0]));
+    }
+}
+
+/* interpolate_gpu.cu:116-143 (atomicAdd order unspecified; here j-ascending) */
+void bqa_oracle_three_interpolate_grad(int b, int c, int n, int m, const float *grad_out,
+                                       const int *idx, const float *weight, float *grad_points) {
+  memset(grad_points, 0, sizeof(float) * (size_t)b * c * m);
+#pragma omp parallel for collapse(2)
+  for (int i = 0; i < b; i++)
+    for (int l = 0; l < c; l++) {
+      float *g = grad_points + ((size_t)i * c + l) * m;
+      const int *ix = idx + (size_t)i * n * 3;
+      const float *w = weight + (size_t)i * n * 3;
+      const float *go = grad_out + ((size_t)i * c + l) * n;
+      for (int j = 0; j < n; j++) {
+        g[ix[j * 3 + 0]] += go[j] * w[j * 3 + 0];
+        g[ix[j * 3 + 1]] += go[j] * w[j * 3 + 1];
+        g[ix[j * 3 + 2]] += go[j] * w[j * 3 + 2];
+      }
+    }
+}
+
+/* host thread count actually used by the OpenMP loops above */
+int bqa_oracle_num_threads(void) {
+#ifdef _OPENMP
+  extern int omp_get_max_threads(void);
+  return omp_get_max_threads();
+#else
+  return 1;
+#endif
+}
+
+void bqa_oracle_set_num_threads(int t) {
+#ifdef _OPENMP
+  extern void omp_set_num_threads(int);
+  if (t > 0) omp_set_num_threads(t);
+#else
+  (void)t;
+#endif
+}

@@ -1,0 +1,217 @@
+"""CPU-only checks of the oracle (oracle/pointnet2_oracle.c + oracle/modules_cpu.py):
+against the committed golden vectors (outputs of the reference's CUDA extension and of the
+reference's Python layer) and against independent brute-force / literal re-simulations."""
+import glob
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from bridgeqa_b200 import synthetic
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def scenes(b, n, first=0):
+    return synthetic.make_batch(b, n, 0, first_scene=first)[..., :3].contiguous().numpy()
+
+
+# ---- literal simulation of the reference FPS kernel (threads + tree), tiny sizes only ----
+
+def fps_literal(xyz, m, block_size):
+    """Pure-Python transliteration of sampling_gpu.cu:69-173 with `block_size` threads,
+    float32 arithmetic with an exact fma emulated in float64 (products of float32 are exact
+    in float64; one rounding per fma step)."""
+    f32 = np.float32
+
+    def fma(a, b, c):
+        return f32(np.float64(a) * np.float64(b) + np.float64(c))
+
+    n = xyz.shape[0]
+    temp = np.full(n, 1e10, dtype=np.float32)
+    idxs = np.zeros(m, dtype=np.int32)
+    old = 0
+    for j in range(1, m):
+        dists = np.full(block_size, -1.0, dtype=np.float32)
+        dists_i = np.zeros(block_size, dtype=np.int64)
+        x1, y1, z1 = xyz[old]
+        for tid in range(block_size):
+            best, besti = f32(-1), 0
+            for k in range(tid, n, block_size):
+                x2, y2, z2 = xyz[k]
+                mag = fma(z2, z2, fma(y2, y2, f32(x2 * x2)))
+                if np.float64(mag) <= 1e-3:
+                    continue
+                dx, dy, dz = f32(x2 - x1), f32(y2 - y1), f32(z2 - z1)
+                d = fma(dz, dz, fma(dy, dy, f32(dx * dx)))
+                d2 = min(d, temp[k])
+                temp[k] = d2
+                if d2 > best:
+                    besti, best = k, d2
+            dists[tid], dists_i[tid] = best, besti
+        s = block_size // 2
+        while s >= 1:
+            for tid in range(s):
+                v1, v2 = dists[tid], dists[tid + s]
+                i1, i2 = dists_i[tid], dists_i[tid + s]
+                dists[tid] = max(v1, v2)
+                dists_i[tid] = i2 if v2 > v1 else i1
+            s //= 2
+        old = int(dists_i[0])
+        idxs[j] = old
+    return idxs
+
+
+@pytest.mark.parametrize("n,m", [(40, 12), (130, 20), (600, 24)])
+def test_fps_oracle_equals_literal_kernel_simulation(oracle_ops, n, m):
+    rng = np.random.default_rng(n)
+    xyz = rng.integers(-3, 4, (n, 3)).astype(np.float32) * np.float32(0.5)   # lattice: many ties
+    xyz[::9] *= np.float32(0.01)                                             # skipped points
+    bs = oracle_ops.opt_n_threads(n)
+    want = fps_literal(xyz, m, bs)
+    got = oracle_ops.furthest_point_sampling(xyz[None], m)[0]
+    np.testing.assert_array_equal(got, want)
+
+
+def test_opt_n_threads_rule(oracle_ops):
+    for n, want in [(1, 1), (2, 2), (3, 2), (511, 256), (512, 512), (513, 512), (1024, 512),
+                    (2048, 512), (20000, 512), (40000, 512), (100000, 512)]:
+        assert oracle_ops.opt_n_threads(n) == want
+
+
+def test_fps_tie_break_is_bitrev_order(oracle_ops):
+    """All points equidistant from point 0 except point 0 itself: the second pick is the tied
+    point minimising (bitrev9(k mod 512), k) -- SURVEY.md 8a rule 5."""
+    n = 1500
+    ang = np.linspace(0, 2 * np.pi, n, endpoint=False)
+    xyz = np.zeros((1, n, 3), dtype=np.float32)
+    # points on a lattice sphere would not be exactly equidistant; use two values only
+    xyz[0, :, 0] = 1.0
+    xyz[0, 0] = (3.0, 0.0, 0.0)            # seed; everyone else at squared distance 4
+    got = oracle_ops.furthest_point_sampling(xyz, 2)[0]
+
+    def bitrev9(v):
+        return int("{:09b}".format(v)[::-1], 2)
+    cand = min(range(1, n), key=lambda k: (bitrev9(k % 512), k))
+    assert got[1] == cand
+
+
+def test_ball_query_bruteforce(oracle_ops):
+    xyz = scenes(2, 3000, first=4)
+    centres = xyz[:, ::30].copy()
+    centres[:, -3:] += 50.0                       # empty balls
+    r, ns = 0.35, 16
+    got = oracle_ops.ball_query(centres, xyz, r, ns)
+    r2 = np.float32(r) * np.float32(r)
+    for b in range(2):
+        for j in range(0, centres.shape[1], 7):
+            d = (centres[b, j].astype(np.float64) - xyz[b].astype(np.float64))
+            d2 = (d ** 2).sum(-1)
+            # exclude borderline cases from the float64 brute force
+            hits = np.nonzero(d2 < r2)[0]
+            if np.any(np.abs(d2 - r2) < 1e-6):
+                continue
+            row = np.zeros(ns, np.int32)
+            if len(hits):
+                row[:] = hits[0]
+                row[:min(ns, len(hits))] = hits[:ns]
+            np.testing.assert_array_equal(got[b, j], row)
+    assert (got[:, -3:] == 0).all()
+
+
+def test_three_nn_bruteforce(oracle_ops):
+    xyz = scenes(2, 900, first=6)
+    unknown, known = xyz[:, :500], xyz[:, 500:]
+    d2, idx = oracle_ops.three_nn(unknown, known)
+    full = ((unknown[:, :, None].astype(np.float64) - known[:, None].astype(np.float64)) ** 2).sum(-1)
+    order = np.argsort(full, axis=-1, kind="stable")[..., :3]
+    np.testing.assert_allclose(d2, np.take_along_axis(full, order, -1), rtol=1e-5, atol=1e-7)
+    assert (idx == order).mean() > 0.999          # float32 vs float64 near-ties only
+    d2s, idxs = oracle_ops.three_nn(unknown, known[:, :2])
+    assert np.isinf(d2s[..., 2]).all() and (idxs[..., 2] == 0).all()
+
+
+def test_gather_group_interpolate_numpy(oracle_ops):
+    rng = np.random.default_rng(2)
+    pts = rng.standard_normal((2, 5, 300)).astype(np.float32)
+    idx = rng.integers(0, 300, (2, 40, 8)).astype(np.int32)
+    np.testing.assert_array_equal(oracle_ops.group_points(pts, idx),
+                                  np.stack([pts[b][:, idx[b]] for b in range(2)]))
+    g = oracle_ops.gather_points(pts, idx[:, :, 0].copy())
+    np.testing.assert_array_equal(g, np.stack([pts[b][:, idx[b, :, 0]] for b in range(2)]))
+    go = rng.standard_normal((2, 5, 40, 8)).astype(np.float32)
+    want = np.zeros((2, 5, 300), np.float64)
+    for b in range(2):
+        for c in range(5):
+            np.add.at(want[b, c], idx[b].reshape(-1), go[b, c].reshape(-1))
+    np.testing.assert_allclose(oracle_ops.group_points_grad(go, idx, 300), want, rtol=1e-5, atol=1e-5)
+    # the reference's own unit test setting (pointnet2_test.py:18-30)
+    feats = rng.standard_normal((1, 2, 4)).astype(np.float32)
+    i3 = np.array([[[0, 1, 2], [1, 2, 3]]], np.int32)
+    w3 = np.array([[[1, 1, 1], [2, 2, 2]]], np.float32)
+    out = oracle_ops.three_interpolate(feats, i3, w3)
+    np.testing.assert_allclose(out[0, :, 0], feats[0, :, :3].sum(-1), rtol=1e-6)
+    np.testing.assert_allclose(out[0, :, 1], 2 * feats[0, :, 1:].sum(-1), rtol=1e-6)
+    gi = oracle_ops.three_interpolate_grad(np.ones((1, 2, 2), np.float32), i3, w3, 4)
+    np.testing.assert_allclose(gi[0, 0], [1, 3, 3, 2])
+
+
+# ---- golden vectors ---------------------------------------------------------------------
+
+def test_oracle_modules_match_reference_python_layer():
+    """oracle/modules_cpu.py vs outputs of the reference's own pointnet2_modules /
+    backbone_module / voting_module (tests/golden/make_golden_cpu.py)."""
+    from oracle import modules_cpu
+    from bridgeqa_b200 import detector
+    g = np.load(os.path.join(GOLDEN, "ref_python_layer.npz"))
+    B, N, C = int(g["meta_B"]), int(g["meta_N"]), int(g["meta_C"])
+    pc = synthetic.make_batch(B, N, C, first_scene=int(g["meta_first_scene"]))
+    net = synthetic.fill_state_dict(detector.Pointnet2Backbone(input_feature_dim=C),
+                                    seed=int(g["meta_backbone_seed"]))
+    assert sorted(net.state_dict().keys()) == list(g["backbone_keys"])
+    out = modules_cpu.backbone(pc.numpy(), net.state_dict())
+    for k in ("sa1_inds", "sa2_inds", "fp2_inds"):
+        np.testing.assert_array_equal(out[k], g[k], err_msg=k)
+    for k in ("sa1_xyz", "sa2_xyz", "sa3_xyz", "sa4_xyz"):
+        np.testing.assert_array_equal(out[k], g[k], err_msg=k)
+
+    def sample(a, k=4096):
+        flat = np.ascontiguousarray(a).reshape(-1)
+        return flat[::max(1, flat.size // k)][:k]
+
+    for k in ("sa1_features", "sa2_features", "sa3_features", "sa4_features", "fp2_features"):
+        np.testing.assert_allclose(sample(out[k]), g[k + "_sample"], rtol=1e-4, atol=1e-5, err_msg=k)
+        np.testing.assert_allclose(np.abs(out[k].astype(np.float64)).sum(), g[k + "_abssum"], rtol=1e-5)
+    vote = synthetic.fill_state_dict(detector.VotingModule(1, 256), seed=int(g["meta_voting_seed"]))
+    assert sorted(vote.state_dict().keys()) == list(g["voting_keys"])
+    vxyz, vfeat = modules_cpu.voting(out["fp2_xyz"], out["fp2_features"], vote.state_dict(), "")
+    np.testing.assert_allclose(vxyz, g["vote_xyz"], rtol=1e-4, atol=1e-5)
+    np.testing.assert_allclose(sample(vfeat), g["vote_features_sample"], rtol=1e-4, atol=1e-5)
+
+
+def test_oracle_matches_reference_extension_golden(oracle_ops):
+    """tests/golden/ref_ext_*.npz hold outputs of the reference's CUDA extension run on the
+    B200 box (tests/golden/make_golden_gpu.py); the C oracle must reproduce them bit for bit."""
+    files = sorted(glob.glob(os.path.join(GOLDEN, "ref_ext_*.npz")))
+    if not files:
+        pytest.skip("no reference-extension golden files committed yet")
+    for path in files:
+        g = np.load(path)
+        xyz = scenes(int(g["B"]), int(g["N"]), first=int(g["first_scene"]))
+        inds = oracle_ops.furthest_point_sampling(xyz, int(g["npoint"]))
+        np.testing.assert_array_equal(inds, g["fps_inds"], err_msg=path)
+        centres = np.take_along_axis(xyz, inds[..., None].astype(np.int64), 1)
+        bq = oracle_ops.ball_query(centres, xyz, float(g["radius"]), int(g["nsample"]))
+        np.testing.assert_array_equal(bq, g["ball_idx"], err_msg=path)
+        m = int(g["nn_m"])
+        d2, idx = oracle_ops.three_nn(centres, np.ascontiguousarray(centres[:, :m]))
+        np.testing.assert_array_equal(idx, g["nn_idx"], err_msg=path)
+        np.testing.assert_array_equal(d2, g["nn_dist2"], err_msg=path)
+        w = (1.0 / (np.sqrt(d2) + np.float32(1e-8))).astype(np.float32)
+        w = (w / w.sum(-1, keepdims=True)).astype(np.float32)
+        feats = np.ascontiguousarray(xyz[:, :m].transpose(0, 2, 1))
+        np.testing.assert_array_equal(oracle_ops.three_interpolate(feats, idx, g["nn_weight"]),
+                                      g["interp"], err_msg=path)
+        grouped = oracle_ops.group_points(np.ascontiguousarray(xyz.transpose(0, 2, 1)), bq)
+        np.testing.assert_array_equal(grouped[:, :, ::16], g["grouped_xyz_strided"], err_msg=path)
