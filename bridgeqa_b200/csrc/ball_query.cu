@@ -11,7 +11,7 @@
 // Hits are appended in ascending k, so the row is "the first nsample hits"; the
 // reference's "first hit back-fills the whole row" is applied once at the end.
 //
-// Bit-exact: d2 = fma(dz,dz,fma(dy,dy,dx*dx)) (nvcc's contraction of
+// Bit-exact: d2 = fma(dz,dz,fma(dx,dx,dy*dy)) (nvcc's contraction of
 // ball_query_gpu.cu:30-31), compared `<` against radius*radius computed in fp32.
 #include "common.cuh"
 

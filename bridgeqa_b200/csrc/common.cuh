@@ -106,11 +106,12 @@ __device__ __forceinline__ void st_async_b32(uint32_t remote_addr, uint32_t a,
                : "memory");
 }
 
-// the reference's distance: nvcc contracts (a-b)^2 sums to fma(dz,dz,fma(dy,dy,dx*dx))
+// the reference's distance: nvcc 12.9 contracts dx*dx + dy*dy + dz*dz to
+// fma(dz,dz, fma(dx,dx, dy*dy)) -- the middle product is the lone FMUL (reference SASS)
 __device__ __forceinline__ float sqdist3(float ax, float ay, float az, float bx, float by,
                                          float bz) {
   const float dx = ax - bx, dy = ay - by, dz = az - bz;
-  return __fmaf_rn(dz, dz, __fmaf_rn(dy, dy, __fmul_rn(dx, dx)));
+  return __fmaf_rn(dz, dz, __fmaf_rn(dx, dx, __fmul_rn(dy, dy)));
 }
 
 #endif  // __CUDACC__

@@ -17,7 +17,7 @@
 //   * the winner's coordinates ride along, so the gather of new_xyz is free.
 //
 // Bit-exact contract with the reference:
-//   d = fma(dz,dz,fma(dy,dy,dx*dx)), temp = min(d,temp), points with
+//   d = fma(dz,dz,fma(dx,dx,dy*dy)), temp = min(d,temp), points with
 //   (double)|p|^2 <= 1e-3 never update and are never selected, and among equal maxima
 //   the winner minimises (bitrev(k mod bs), k) where bs = opt_n_threads(n) is the block
 //   size the reference would have used -- that is what its pairwise tree with
@@ -99,7 +99,7 @@ fps_cluster_kernel(int n, int m, int cs, int bits, const float *__restrict__ xyz
       x = xyz[(size_t)k * 3 + 0];
       y = xyz[(size_t)k * 3 + 1];
       z = xyz[(size_t)k * 3 + 2];
-      const float mag = __fmaf_rn(z, z, __fmaf_rn(y, y, __fmul_rn(x, x)));
+      const float mag = __fmaf_rn(z, z, __fmaf_rn(x, x, __fmul_rn(y, y)));
       if (!((double)mag <= 1e-3)) t = 1e10f;  // sampling_gpu.cu:100-101, sampling.cpp:74-76
     }
     px[p] = x; py[p] = y; pz[p] = z; td[p] = t;
@@ -132,7 +132,7 @@ fps_cluster_kernel(int n, int m, int cs, int bits, const float *__restrict__ xyz
 #pragma unroll
     for (int p = 0; p < P; ++p) {
       const float dx = px[p] - x1, dy = py[p] - y1, dz = pz[p] - z1;
-      const float d = __fmaf_rn(dz, dz, __fmaf_rn(dy, dy, __fmul_rn(dx, dx)));
+      const float d = __fmaf_rn(dz, dz, __fmaf_rn(dx, dx, __fmul_rn(dy, dy)));
       const float d2 = fminf(d, td[p]);
       td[p] = d2;
       if (d2 > best) { best = d2; bslot = p; }   // strict: lowest k wins inside a thread
@@ -220,7 +220,7 @@ fps_global_kernel(int n, int m, int bits, const float *__restrict__ xyz_all,
   float *new_xyz = new_xyz_all ? new_xyz_all + (size_t)scene * m * 3 : nullptr;
   for (int k = tid; k < n; k += 1024) {
     const float x = xyz[(size_t)k * 3], y = xyz[(size_t)k * 3 + 1], z = xyz[(size_t)k * 3 + 2];
-    const float mag = __fmaf_rn(z, z, __fmaf_rn(y, y, __fmul_rn(x, x)));
+    const float mag = __fmaf_rn(z, z, __fmaf_rn(x, x, __fmul_rn(y, y)));
     temp[k] = ((double)mag <= 1e-3) ? -INFINITY : 1e10f;
   }
   uint32_t old = 0;

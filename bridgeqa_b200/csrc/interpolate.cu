@@ -5,10 +5,10 @@
 // shared-memory tiles of the known set (three_nn); one thread per output column with a
 // channel slab per CTA (three_interpolate), so index/weight rows are read once per slab.
 //
-// Bit-exact: d = fma(dz,dz,fma(dy,dy,dx*dx)); strict `<` cascade in ascending k
+// Bit-exact: d = fma(dz,dz,fma(dx,dx,dy*dy)); strict `<` cascade in ascending k
 // (lowest index wins ties); fewer than 3 known points leave dist2 = +inf (the
 // reference's (float)1e40) and idx = 0.  Interpolation is
-// fma(p3,w3,fma(p2,w2,p1*w1)), the contraction nvcc emits for interpolate_gpu.cu:99-100.
+// fma(p3,w3,fma(p1,w1,p2*w2)), the contraction nvcc emits for interpolate_gpu.cu:99-100.
 #include "common.cuh"
 
 namespace bqa {
@@ -80,7 +80,7 @@ three_interpolate_kernel(int c, int m, int n, const float *__restrict__ points,
   for (int l = l0; l < lend; ++l) {
     const float *p = points + ((size_t)scene * c + l) * m;
     out[((size_t)scene * c + l) * n + j] =
-        __fmaf_rn(__ldg(p + a3), w3, __fmaf_rn(__ldg(p + a2), w2, __fmul_rn(__ldg(p + a1), w1)));
+        __fmaf_rn(__ldg(p + a3), w3, __fmaf_rn(__ldg(p + a1), w1, __fmul_rn(__ldg(p + a2), w2)));
   }
 }
 

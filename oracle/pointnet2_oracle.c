@@ -17,8 +17,10 @@
  *
  * Arithmetic rules that make the results bit-identical to the nvcc build of
  * the reference (checked against its sm_100a SASS):
- *   - nvcc contracts  a*a + b*b + c*c  to  fma(c,c, fma(b,b, a*a))  in fp32;
- *     this file is compiled with -ffp-contract=off and spells each fmaf().
+ *   - nvcc 12.9 contracts  t0 + t1 + t2  (three products, parsed (t0+t1)+t2) to
+ *     fma(t2a,t2b, fma(t0a,t0b, t1a*t1b)): the MIDDLE product is the lone FMUL (read off
+ *     the SASS of all four reference kernels: FMUL on the y term, FFMA x, FFMA z).
+ *     This file is compiled with -ffp-contract=off and spells each fmaf().
  *   - `mag <= 1e-3` compares (double)mag with the double literal.
  *   - three_nn keeps its running bests in double, starting at 1e40.
  *   - FPS reduces 512 per-thread partials with a 9-step pairwise tree in which
@@ -47,7 +49,7 @@ int bqa_oracle_opt_n_threads(int work_size) {
 static inline float sqdist(float ax, float ay, float az, float bx, float by, float bz) {
   /* (a-b)*(a-b) + ... as nvcc contracts it */
   const float dx = ax - bx, dy = ay - by, dz = az - bz;
-  return fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+  return fmaf(dz, dz, fmaf(dx, dx, dy * dy));
 }
 
 /* ------------------------------------------------------------------ FPS --- */
@@ -68,10 +70,10 @@ HOT static void fps_one_scene(int n, int m, const float *xyz, float *temp, int *
       for (int t = 0; t < lim; t++) {
         const int k = base + t;
         const float x2 = xyz[k * 3 + 0], y2 = xyz[k * 3 + 1], z2 = xyz[k * 3 + 2];
-        const float mag = fmaf(z2, z2, fmaf(y2, y2, x2 * x2));        /* :100 */
+        const float mag = fmaf(z2, z2, fmaf(x2, x2, y2 * y2));        /* :100 */
         if ((double)mag <= 1e-3) continue;                            /* :101 */
         const float dx = x2 - x1, dy = y2 - y1, dz = z2 - z1;          /* :103-104 */
-        const float d = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+        const float d = fmaf(dz, dz, fmaf(dx, dx, dy * dy));
         const float d2 = fminf(d, temp[k]);                           /* :106 */
         temp[k] = d2;                                                 /* :107 */
         if (d2 > best[t]) { besti[t] = k; best[t] = d2; }             /* :108-109 */
@@ -219,7 +221,7 @@ HOT void bqa_oracle_three_nn(int b, int n, int m, const float *unknown, const fl
 
 /* -------------------------------------------------- three_interpolate --- */
 /* interpolate_gpu.cu:72-101: points (b,c,m), idx (b,n,3), weight (b,n,3) -> out (b,c,n)
- * p1*w1 + p2*w2 + p3*w3  contracts to  fma(p3,w3, fma(p2,w2, p1*w1)). */
+ * p1*w1 + p2*w2 + p3*w3  contracts to  fma(p3,w3, fma(p1,w1, p2*w2)). */
 HOT void bqa_oracle_three_interpolate(int b, int c, int m, int n, const float *points,
                                       const int *idx, const float *weight, float *out) {
 #pragma omp parallel for collapse(2)
@@ -231,7 +233,7 @@ HOT void bqa_oracle_three_interpolate(int b, int c, int m, int n, const float *p
       float *o = out + ((size_t)i * c + l) * n;
       for (int j = 0; j < n; j++)
         o[j] = fmaf(p[ix[j * 3 + 2]], w[j * 3 + 2],
-                    fmaf(p[ix[j * 3 + 1]], w[j * 3 + 1], p[ix[j * 3 + 0]] * w[j * 3 + 0]));
+                    fmaf(p[ix[j * 3 + 0]], w[j * 3 + 0], p[ix[j * 3 + 1]] * w[j * 3 + 1]));
     }
 }
 

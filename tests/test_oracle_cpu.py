@@ -40,11 +40,11 @@ def fps_literal(xyz, m, block_size):
             best, besti = f32(-1), 0
             for k in range(tid, n, block_size):
                 x2, y2, z2 = xyz[k]
-                mag = fma(z2, z2, fma(y2, y2, f32(x2 * x2)))
+                mag = fma(z2, z2, fma(x2, x2, f32(y2 * y2)))
                 if np.float64(mag) <= 1e-3:
                     continue
                 dx, dy, dz = f32(x2 - x1), f32(y2 - y1), f32(z2 - z1)
-                d = fma(dz, dz, fma(dy, dy, f32(dx * dx)))
+                d = fma(dz, dz, fma(dx, dx, f32(dy * dy)))
                 d2 = min(d, temp[k])
                 temp[k] = d2
                 if d2 > best:
