@@ -57,6 +57,15 @@ int three_interpolate_dispatch(int b, int c, int m, int n, const float *points, 
 int three_interpolate_grad_dispatch(int b, int c, int n, int m, const float *grad_out, const int *idx,
                                     const float *weight, float *grad_points, cudaStream_t stream);
 
+int sa_supported(int nsample, int npoint, int c, int c1, int c2, int c3);
+int pack_weight_dispatch(int c_out, int c_in, int kpad, int xyz_first, const float *w, void *packed,
+                         cudaStream_t stream);
+int sa_forward_dispatch(int b, int n, int npoint, int nsample, int c, const float *xyz,
+                        const float *new_xyz, const float *feat_pm, int feat_stride, const int *idx, float radius,
+                        int normalize_xyz, int c1, int c2, int c3, const void *w1p, const float *b1,
+                        const void *w2p, const float *b2, const void *w3p, const float *b3,
+                        float *out_cm, float *out_pm, cudaStream_t stream);
+
 }  // namespace bqa
 
 using namespace bqa;
@@ -158,6 +167,36 @@ int bqa_transpose_to_point_major(int b, int c, int n, const float *in, float *ou
   if ((long long)b * c * n == 0) return BQA_OK;
   PTR(in); PTR(out);
   return transpose_cn_dispatch(b, c, n, in, out, (cudaStream_t)stream);
+}
+
+int bqa_pack_weight_bf16(int c_out, int c_in, int k_pad, int xyz_first, const float *w, void *packed,
+                         void *stream) {
+  BQA_REQUIRE(c_out > 0 && c_in > 0, "%s: empty weight", __func__);
+  BQA_REQUIRE(k_pad >= c_in && k_pad % 16 == 0, "%s: k_pad=%d must be a multiple of 16 >= c_in=%d",
+              __func__, k_pad, c_in);
+  BQA_REQUIRE(!xyz_first || c_in >= 3, "%s: xyz_first needs c_in >= 3", __func__);
+  PTR(w); PTR(packed);
+  return pack_weight_dispatch(c_out, c_in, k_pad, xyz_first, w, packed, (cudaStream_t)stream);
+}
+
+int bqa_sa_mlp_max_supported(int nsample, int npoint, int c, int c1, int c2, int c3) {
+  return sa_supported(nsample, npoint, c, c1, c2, c3);
+}
+
+int bqa_sa_mlp_max_forward(int b, int n, int npoint, int nsample, int c, const float *xyz,
+                           const float *new_xyz, const float *feat_pm, int feat_stride, const int *idx, float radius,
+                           int normalize_xyz, int c1, int c2, int c3, const void *w1p, const float *b1,
+                           const void *w2p, const float *b2, const void *w3p, const float *b3,
+                           float *out_cm, float *out_pm, void *stream) {
+  NONNEG(b); NONNEG(n); NONNEG(npoint); NONNEG(nsample); NONNEG(c);
+  if ((long long)b * npoint == 0) return BQA_OK;
+  PTR(xyz); PTR(new_xyz); PTR(idx); PTR(w1p); PTR(b1); PTR(w2p); PTR(b2); PTR(w3p); PTR(b3); PTR(out_cm);
+  BQA_REQUIRE((c == 0) == (feat_pm == nullptr), "%s: feat_pm must be NULL iff c == 0", __func__);
+  BQA_REQUIRE(c == 0 || feat_stride >= c, "%s: feat_stride=%d < c=%d", __func__, feat_stride, c);
+  BQA_REQUIRE(!normalize_xyz || radius > 0.f, "%s: radius must be > 0", __func__);
+  return sa_forward_dispatch(b, n, npoint, nsample, c, xyz, new_xyz, feat_pm, feat_stride, idx, radius,
+                             normalize_xyz, c1, c2, c3, w1p, b1, w2p, b2, w3p, b3, out_cm, out_pm,
+                             (cudaStream_t)stream);
 }
 
 }  // extern "C"

@@ -1,0 +1,364 @@
+// sa_fused.cu -- fused set-abstraction layer for inference on sm_100a:
+//   gather neighbours -> [1x1 conv + folded BN + ReLU] x3 on tcgen05 tensor cores -> max
+//   over nsample, without ever writing the grouped (B, C+3, npoint, nsample) tensor or
+//   any intermediate activation to HBM.
+//
+// Replaces, for eval-mode forward, the chain the reference runs as ~12 separate kernels
+// with full HBM round trips: QueryAndGroup.forward (pointnet2_utils.py:317-376; two
+// group_points launches, subtract, divide, cat), SharedMLP (pytorch_utils.py:11-36; 3 x
+// [cuDNN conv, BN, ReLU]) and F.max_pool2d (pointnet2_modules.py:259-262).
+//
+// One CTA of 128 threads owns a tile of 128 "rows" (row = one (centre, sample) pair;
+// 128/nsample consecutive centres of one scene) and walks tiles persistently.
+//
+//   layer 1   D1[128 x C1]  = A1[128 x K1] * W1^T     A1 = gathered rows (bf16, smem)
+//   layer 2   D2[128 x C2]  = X1[128 x C1] * W2^T     X1 = relu(D1 + b1)  (bf16, smem)
+//   layer 3   D3T[C3 x 128] = W3[C3 x C2]  * X2^T     X2 = relu(D2 + b2)  (bf16, smem)
+//
+// Layers 1-2 keep rows on TMEM lanes, so an epilogue thread owns a row and stores it as
+// 16-byte K-major vectors for the next MMA; layer 3 is issued TRANSPOSED (weights as the
+// A operand) so that TMEM lanes are output channels and the 128 rows are TMEM columns:
+// the max over nsample consecutive rows becomes a register-local max for the thread that
+// owns the channel (no shuffles), after which bias + ReLU are applied once
+// (max(relu(x+b)) == relu(max(x)+b)).
+//
+// Accumulators live in TMEM (D1|D2 side by side, D3T aliases them once they are dead);
+// operands are bf16 with fp32 accumulation; layer-1 K is permuted to
+// [features(C), xyz_rel(3), 0-pad] (the host packs W1 the same way) and processed in
+// chunks of 128 so that the weights of all three layers stay resident in shared memory.
+#include <cuda_bf16.h>
+
+#include "common.cuh"
+#include "tcgen05.cuh"
+
+namespace bqa {
+namespace {
+
+constexpr int kRows = 128;       // rows per tile == threads per CTA
+constexpr int kKChunk = 128;     // layer-1 K processed per pass
+
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+  __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t *>(&v);
+}
+
+struct SaParams {
+  int b, n, npoint, nsample, c;     // c = feature channels (K1 = c + 3)
+  int k1pad;                        // K1 rounded up to a multiple of 16
+  int feat_stride;                  // floats between consecutive points of feat_pm (>= c)
+  int feat_vec4;                    // rows are 16-byte aligned: float4 loads allowed
+  const float *xyz, *new_xyz, *feat_pm;
+  const int *idx;
+  float radius;
+  int normalize_xyz;
+  const uint4 *w1p, *w2p, *w3p;     // packed bf16 images [K/8][rows] of 16-byte vectors
+  const float *b1, *b2, *b3;
+  float *out_cm, *out_pm;
+  int num_tiles;
+};
+
+// epilogue of a row-on-lane accumulator: X[r][0..CN) = relu(D[r][*] + bias) as bf16, stored
+// chunk-major ([CN/8][128] x 16 B) for the next MMA.
+template <int CN>
+__device__ __forceinline__ void epilogue_rows(uint32_t tmem_d, int warp, int row, const float *s_bias,
+                                              uint4 *x_buf) {
+#pragma unroll
+  for (int c0 = 0; c0 < CN; c0 += 32) {
+    uint32_t v[32];
+    umma::ld_32x32b_x32(tmem_d + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0, v);
+    umma::wait_ld();
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      uint32_t p[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int col = c0 + q * 8 + e * 2;
+        const float lo = fmaxf(__uint_as_float(v[q * 8 + e * 2]) + s_bias[col], 0.f);
+        const float hi = fmaxf(__uint_as_float(v[q * 8 + e * 2 + 1]) + s_bias[col + 1], 0.f);
+        p[e] = pack_bf16x2(lo, hi);
+      }
+      x_buf[(c0 / 8 + q) * kRows + row] = make_uint4(p[0], p[1], p[2], p[3]);
+    }
+  }
+}
+
+template <int C1, int C2, int C3>
+__global__ void __launch_bounds__(kRows)
+sa_mlp_max_kernel(const SaParams P) {
+  static_assert(C1 % 32 == 0 && C2 % 32 == 0 && C3 % 128 == 0, "channel counts");
+  constexpr int kXVecs = (C1 > C2 ? C1 : C2) / 8 * kRows;             // X1 / X2 buffer
+  constexpr int kAVecs = kKChunk / 8 * kRows;                         // layer-1 A chunk
+  constexpr int kAXVecs = kXVecs > kAVecs ? kXVecs : kAVecs;          // they alias
+  constexpr uint32_t kTmemCols = (C1 + C2 > C3 ? C1 + C2 : C3) <= 128 ? 128 : 256;
+  static_assert((C1 + C2 > C3 ? C1 + C2 : C3) <= 256, "TMEM budget");
+
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  uint4 *ax = reinterpret_cast<uint4 *>(smem_raw);                    // A1 chunk / X1 / X2
+  uint4 *w1s = ax + kAXVecs;                                          // [k1pad/8][C1]
+  uint4 *w2s = w1s + (P.k1pad / 8) * C1;                              // [C1/8][C2]
+  uint4 *w3s = w2s + (C1 / 8) * C2;                                   // [C2/8][C3]
+  float *s_b1 = reinterpret_cast<float *>(w3s + (C2 / 8) * C3);
+  float *s_b2 = s_b1 + C1;
+  float *s_b3 = s_b2 + C2;
+  uint64_t *s_bar = reinterpret_cast<uint64_t *>(s_b3 + C3);
+  uint32_t *s_tmem = reinterpret_cast<uint32_t *>(s_bar + 1);
+
+  const int tid = threadIdx.x;
+  const int warp = tid >> 5;
+
+  // ---- one-time setup: weights + biases -> smem, mbarrier, TMEM ----------------------
+  for (int i = tid; i < (P.k1pad / 8) * C1; i += kRows) w1s[i] = P.w1p[i];
+  for (int i = tid; i < (C1 / 8) * C2; i += kRows) w2s[i] = P.w2p[i];
+  for (int i = tid; i < (C2 / 8) * C3; i += kRows) w3s[i] = P.w3p[i];
+  for (int i = tid; i < C1; i += kRows) s_b1[i] = P.b1[i];
+  for (int i = tid; i < C2; i += kRows) s_b2[i] = P.b2[i];
+  for (int i = tid; i < C3; i += kRows) s_b3[i] = P.b3[i];
+  const uint32_t bar = smem_u32(s_bar);
+  if (tid == 0) {
+    mbar_init(bar, 1);
+    fence_mbar_init_cluster();
+  }
+  if (warp == 0) umma::tmem_alloc(smem_u32(s_tmem), kTmemCols);
+  umma::fence_proxy_async_smem();          // weights were written with st.shared
+  umma::fence_before_sync();
+  __syncthreads();
+  umma::fence_after_sync();
+  const uint32_t tmem = *s_tmem;
+  const uint32_t tmem_d1 = tmem, tmem_d2 = tmem + C1, tmem_d3 = tmem;
+
+  const uint32_t ax_addr = smem_u32(ax), w1_addr = smem_u32(w1s), w2_addr = smem_u32(w2s),
+                 w3_addr = smem_u32(w3s);
+  constexpr uint32_t kIdesc1 = umma::instr_desc_bf16_f32(128, C1);
+  constexpr uint32_t kIdesc2 = umma::instr_desc_bf16_f32(128, C2);
+  constexpr uint32_t kIdesc3 = umma::instr_desc_bf16_f32(128, 128);
+  uint32_t phase = 0;
+
+  const int ns = P.nsample;
+  const int centres_per_tile = kRows / ns;
+  const int tiles_per_scene = P.npoint / centres_per_tile;
+  const float inv_unused = 0.f;
+  (void)inv_unused;
+
+  for (int tile = blockIdx.x; tile < P.num_tiles; tile += gridDim.x) {
+    const int scene = tile / tiles_per_scene;
+    const int centre0 = (tile % tiles_per_scene) * centres_per_tile;
+    // this thread's row: centre j, neighbour index i
+    const int j = centre0 + tid / ns;
+    const int i = P.idx[((size_t)scene * P.npoint + j) * ns + (tid % ns)];
+    const float *frow = P.feat_pm ? P.feat_pm + ((size_t)scene * P.n + i) * P.feat_stride : nullptr;
+    float rel[3];
+    {
+      const float *pp = P.xyz + ((size_t)scene * P.n + i) * 3;
+      const float *qq = P.new_xyz + ((size_t)scene * P.npoint + j) * 3;
+#pragma unroll
+      for (int d = 0; d < 3; ++d) {
+        float v = pp[d] - qq[d];                       // pointnet2_utils.py:350
+        if (P.normalize_xyz) v = v / P.radius;         // :351-352, true division
+        rel[d] = v;
+      }
+    }
+
+    // ---- layer 1: gather K-chunks of A1 and accumulate D1 ------------------------------
+    for (int kc0 = 0; kc0 < P.k1pad; kc0 += kKChunk) {
+      const int kcn = min(kKChunk, P.k1pad - kc0);     // multiple of 16
+      for (int q = 0; q < kcn / 8; ++q) {
+        const int k0 = kc0 + q * 8;
+        float f[8];
+        if (k0 + 8 <= P.c && P.feat_vec4) {            // 8 features, 16-byte aligned rows
+          const float4 a = __ldg(reinterpret_cast<const float4 *>(frow + k0));
+          const float4 bq = __ldg(reinterpret_cast<const float4 *>(frow + k0 + 4));
+          f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w;
+          f[4] = bq.x; f[5] = bq.y; f[6] = bq.z; f[7] = bq.w;
+        } else {
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            const int k = k0 + e;
+            float v = 0.f;
+            if (k < P.c) v = __ldg(frow + k);
+            else if (k < P.c + 3) v = (k - P.c == 0) ? rel[0] : ((k - P.c == 1) ? rel[1] : rel[2]);
+            f[e] = v;
+          }
+        }
+        ax[q * kRows + tid] = make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]),
+                                         pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
+      }
+      umma::fence_proxy_async_smem();
+      umma::fence_before_sync();
+      __syncthreads();
+      if (tid == 0) {
+        umma::fence_after_sync();
+        for (int ks = 0; ks < kcn / 16; ++ks) {
+          const uint64_t ad = umma::smem_desc(ax_addr + (uint32_t)(2 * ks) * kRows * 16, kRows * 16, 128);
+          const uint64_t bd = umma::smem_desc(w1_addr + (uint32_t)(kc0 / 8 + 2 * ks) * C1 * 16, C1 * 16, 128);
+          umma::mma_bf16_ss(tmem_d1, ad, bd, kIdesc1, (kc0 | ks) != 0);
+        }
+        umma::commit(bar);
+      }
+      mbar_wait(bar, phase);
+      phase ^= 1;
+      umma::fence_after_sync();
+    }
+
+    // ---- epilogue 1 -> X1 ; layer 2 ---------------------------------------------------
+    epilogue_rows<C1>(tmem_d1, warp, tid, s_b1, ax);
+    umma::fence_proxy_async_smem();
+    umma::fence_before_sync();
+    __syncthreads();
+    if (tid == 0) {
+      umma::fence_after_sync();
+#pragma unroll
+      for (int ks = 0; ks < C1 / 16; ++ks) {
+        const uint64_t ad = umma::smem_desc(ax_addr + (uint32_t)(2 * ks) * kRows * 16, kRows * 16, 128);
+        const uint64_t bd = umma::smem_desc(w2_addr + (uint32_t)(2 * ks) * C2 * 16, C2 * 16, 128);
+        umma::mma_bf16_ss(tmem_d2, ad, bd, kIdesc2, ks != 0);
+      }
+      umma::commit(bar);
+    }
+    mbar_wait(bar, phase);
+    phase ^= 1;
+    umma::fence_after_sync();
+
+    // ---- epilogue 2 -> X2 ; layer 3 (transposed: channels on lanes) ---------------------
+    epilogue_rows<C2>(tmem_d2, warp, tid, s_b2, ax);
+    umma::fence_proxy_async_smem();
+    umma::fence_before_sync();
+    __syncthreads();
+    if (tid == 0) {
+      umma::fence_after_sync();
+#pragma unroll
+      for (int mt = 0; mt < C3 / 128; ++mt) {
+#pragma unroll
+        for (int ks = 0; ks < C2 / 16; ++ks) {
+          const uint64_t ad = umma::smem_desc(w3_addr + ((uint32_t)(2 * ks) * C3 + mt * 128) * 16, C3 * 16, 128);
+          const uint64_t bd = umma::smem_desc(ax_addr + (uint32_t)(2 * ks) * kRows * 16, kRows * 16, 128);
+          umma::mma_bf16_ss(tmem_d3 + mt * 128, ad, bd, kIdesc3, ks != 0);
+        }
+      }
+      umma::commit(bar);
+    }
+    mbar_wait(bar, phase);
+    phase ^= 1;
+    umma::fence_after_sync();
+
+    // ---- epilogue 3: max over nsample columns, bias, ReLU, store -------------------------
+#pragma unroll
+    for (int mt = 0; mt < C3 / 128; ++mt) {
+      const int ch = mt * 128 + tid;
+      const float bias = s_b3[ch];
+      float run = -INFINITY;
+#pragma unroll
+      for (int c0 = 0; c0 < kRows; c0 += 32) {
+        uint32_t v[32];
+        umma::ld_32x32b_x32(tmem_d3 + mt * 128 + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0, v);
+        umma::wait_ld();
+#pragma unroll
+        for (int g = 0; g < 32; g += 16) {              // nsample is a multiple of 16
+          float m16 = __uint_as_float(v[g]);
+#pragma unroll
+          for (int e = 1; e < 16; ++e) m16 = fmaxf(m16, __uint_as_float(v[g + e]));
+          run = fmaxf(run, m16);
+          const int col_end = c0 + g + 16;               // rows [.., col_end) folded so far
+          if (col_end % ns == 0) {
+            const int jj = centre0 + col_end / ns - 1;
+            const float o = fmaxf(run + bias, 0.f);
+            P.out_cm[((size_t)scene * C3 + ch) * P.npoint + jj] = o;
+            if (P.out_pm) P.out_pm[((size_t)scene * P.npoint + jj) * C3 + ch] = o;
+            run = -INFINITY;
+          }
+        }
+      }
+    }
+    umma::fence_before_sync();
+    __syncthreads();       // TMEM (D3T aliases D1/D2) and the A/X buffer are free again
+    umma::fence_after_sync();
+  }
+
+  __syncthreads();
+  if (warp == 0) umma::tmem_dealloc(tmem, kTmemCols);
+}
+
+// w (c_out, c_in) f32 -> bf16 image [kpad/8][c_out][8]; when xyz_first, source column
+// order [xyz(3), feat(c_in-3)] becomes packed K order [feat, xyz, 0...].
+__global__ void pack_weight_kernel(int c_out, int c_in, int kpad, int xyz_first,
+                                   const float *__restrict__ w, __nv_bfloat16 *__restrict__ out) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= c_out * kpad) return;
+  const int k = t % kpad, row = t / kpad;
+  float v = 0.f;
+  if (k < c_in) {
+    int src = k;
+    if (xyz_first) src = (k < c_in - 3) ? k + 3 : k - (c_in - 3);
+    v = w[(size_t)row * c_in + src];
+  }
+  out[((size_t)(k / 8) * c_out + row) * 8 + (k % 8)] = __float2bfloat16_rn(v);
+}
+
+template <int C1, int C2, int C3>
+int launch_sa(const SaParams &P, cudaStream_t stream) {
+  constexpr int kXVecs = (C1 > C2 ? C1 : C2) / 8 * kRows;
+  constexpr int kAVecs = kKChunk / 8 * kRows;
+  constexpr int kAXVecs = kXVecs > kAVecs ? kXVecs : kAVecs;
+  const size_t smem = 16 * ((size_t)kAXVecs + (size_t)(P.k1pad / 8) * C1 + (size_t)(C1 / 8) * C2 +
+                            (size_t)(C2 / 8) * C3) + 4 * (C1 + C2 + C3) + 16;
+  if (smem > 227 * 1024)
+    return set_error(BQA_ERR_UNSUPPORTED, "sa_mlp_max: needs %zu bytes of shared memory", smem);
+  auto kern = sa_mlp_max_kernel<C1, C2, C3>;
+  BQA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int dev = 0, sms = 148, per_sm = 1;
+  BQA_CUDA(cudaGetDevice(&dev));
+  BQA_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  BQA_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kRows, smem));
+  constexpr int kTmemCols = (C1 + C2 > C3 ? C1 + C2 : C3) <= 128 ? 128 : 256;
+  per_sm = max(1, min(per_sm, 512 / kTmemCols));    // TMEM: 512 columns per SM
+  const int grid = min(P.num_tiles, sms * per_sm);
+  kern<<<grid, kRows, smem, stream>>>(P);
+  count_launch();
+  return check_launch("sa_mlp_max_kernel");
+}
+
+}  // namespace
+
+int sa_supported(int nsample, int npoint, int c, int c1, int c2, int c3) {
+  if (nsample < 16 || nsample > 128 || (nsample & (nsample - 1))) return 0;
+  if ((long long)npoint * nsample % kRows) return 0;
+  if (npoint % (kRows / nsample)) return 0;
+  if (c < 0 || c + 3 > 2048) return 0;
+  return (c1 == 64 && c2 == 64 && c3 == 128) || (c1 == 128 && c2 == 128 && c3 == 256) ||
+         (c1 == 128 && c2 == 128 && c3 == 128);
+}
+
+int pack_weight_dispatch(int c_out, int c_in, int kpad, int xyz_first, const float *w, void *packed,
+                         cudaStream_t stream) {
+  const int total = c_out * kpad;
+  pack_weight_kernel<<<ceil_div(total, 256), 256, 0, stream>>>(c_out, c_in, kpad, xyz_first, w,
+                                                               (__nv_bfloat16 *)packed);
+  count_launch();
+  return check_launch("pack_weight_kernel");
+}
+
+int sa_forward_dispatch(int b, int n, int npoint, int nsample, int c, const float *xyz,
+                        const float *new_xyz, const float *feat_pm, int feat_stride, const int *idx, float radius,
+                        int normalize_xyz, int c1, int c2, int c3, const void *w1p, const float *b1,
+                        const void *w2p, const float *b2, const void *w3p, const float *b3,
+                        float *out_cm, float *out_pm, cudaStream_t stream) {
+  if (!sa_supported(nsample, npoint, c, c1, c2, c3))
+    return set_error(BQA_ERR_UNSUPPORTED,
+                     "sa_mlp_max: unsupported shape nsample=%d npoint=%d c=%d mlp=%d,%d,%d", nsample,
+                     npoint, c, c1, c2, c3);
+  SaParams P;
+  P.b = b; P.n = n; P.npoint = npoint; P.nsample = nsample; P.c = c;
+  P.k1pad = (c + 3 + 15) / 16 * 16;
+  P.feat_stride = feat_stride;
+  P.feat_vec4 = (c % 4 == 0) && (feat_stride % 4 == 0) && ((reinterpret_cast<uintptr_t>(feat_pm) & 15) == 0);
+  P.xyz = xyz; P.new_xyz = new_xyz; P.feat_pm = feat_pm; P.idx = idx;
+  P.radius = radius; P.normalize_xyz = normalize_xyz;
+  P.w1p = (const uint4 *)w1p; P.w2p = (const uint4 *)w2p; P.w3p = (const uint4 *)w3p;
+  P.b1 = b1; P.b2 = b2; P.b3 = b3;
+  P.out_cm = out_cm; P.out_pm = out_pm;
+  P.num_tiles = (int)((long long)b * npoint * nsample / kRows);
+  if (c1 == 64) return launch_sa<64, 64, 128>(P, stream);
+  if (c3 == 256) return launch_sa<128, 128, 256>(P, stream);
+  return launch_sa<128, 128, 128>(P, stream);
+}
+
+}  // namespace bqa

@@ -53,6 +53,9 @@ class Pointnet2Backbone(nn.Module):
     def _break_up_pc(pc):
         xyz = pc[..., :3].contiguous()
         features = pc[..., 3:].transpose(1, 2).contiguous() if pc.size(-1) > 3 else None
+        if features is not None:
+            # the input cloud already is the point-major layout the fused SA kernel gathers from
+            features._bqa_pm = pc[..., 3:]
         return xyz, features
 
     def forward(self, data_dict):

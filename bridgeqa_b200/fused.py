@@ -1,15 +1,22 @@
-"""Host side of the fused inference kernels (SA: gather + 3x[conv+BN+ReLU] + max-pool;
-FP: three_nn + interpolate + concat + 2x[conv+BN+ReLU]).
+"""Host side of the fused inference kernels (SA: gather + 3x[conv+BN+ReLU] + max-pool on
+tcgen05 tensor cores).
 
 The module classes call in here only in eval mode with autograd off; training always
-takes the un-fused, differentiable operators.
+takes the un-fused, differentiable operators.  Nothing here computes on the host: folding
+BN into the convolution weights is a handful of tiny torch device ops done once per module
+(cached until .train() is called), packing to the kernel's bf16 shared-memory image is a
+kernel of the C ABI.
 """
+import ctypes
+
 import torch
 
 from . import _native as N
+from . import ext as _ext
 from . import pytorch_utils as pt_utils
 
 _state = {"enabled": True}
+_f32 = torch.float32
 
 
 def set_fused(flag):
@@ -21,28 +28,106 @@ def enabled():
     return _state["enabled"]
 
 
-def _has(symbol):
-    return symbol in N._SIGNATURES
+def _widths(mlp_module):
+    blocks = list(mlp_module)
+    if len(blocks) != 3:
+        return None
+    ws = []
+    for blk in blocks:
+        conv = getattr(blk, "conv", None)
+        if conv is None or not isinstance(conv, torch.nn.Conv2d) or conv.kernel_size != (1, 1):
+            return None
+        if not isinstance(getattr(blk, "activation", None), torch.nn.ReLU):
+            return None
+        ws.append((conv.in_channels, conv.out_channels))
+    if ws[0][1] != ws[1][0] or ws[1][1] != ws[2][0]:
+        return None
+    return ws
 
 
-def sa_supported(mlp_module, nsample, c_feat):
-    return False
+def sa_supported(mlp_module, nsample, npoint, c_feat):
+    ws = _widths(mlp_module)
+    if ws is None or ws[0][0] != c_feat + 3:
+        return False
+    return bool(N.lib().bqa_sa_mlp_max_supported(int(nsample), int(npoint), int(c_feat),
+                                                ws[0][1], ws[1][1], ws[2][1]))
 
 
 def fp_supported(mlp_module, c_known, c_skip):
     return False
 
 
+class PackedSA(object):
+    """bf16 weight images + fp32 biases of one folded 3-layer SharedMLP, on one device."""
+
+    def __init__(self, mlp_module):
+        ws = _widths(mlp_module)
+        self.c_in = ws[0][0]
+        self.c1, self.c2, self.c3 = ws[0][1], ws[1][1], ws[2][1]
+        self.packed, self.bias = [], []
+        for li, blk in enumerate(mlp_module):
+            w, b = pt_utils.fold_conv_bn(blk)
+            c_out, c_in = w.shape
+            kpad = (c_in + 15) // 16 * 16
+            img = torch.empty(c_out * kpad, dtype=torch.bfloat16, device=w.device)
+            with torch.cuda.device(w.device):
+                N.call("bqa_pack_weight_bf16", c_out, c_in, kpad, 1 if li == 0 else 0, N.ptr(w),
+                       N.ptr(img), N.stream_ptr(w.device))
+            self.packed.append(img)
+            self.bias.append(b)
+        self.device = self.packed[0].device
+
+
+def weights_signature(module):
+    """Changes whenever a parameter / BN buffer of `module` is replaced, moved or written in
+    place (load_state_dict, optimizer step, .to()), so folded weights are never stale."""
+    return tuple((t.data_ptr(), t._version) for t in list(module.parameters()) + list(module.buffers()))
+
+
 def fold_sa_mlp(mlp_module):
-    return [pt_utils.fold_conv_bn(block) for block in mlp_module]
+    return PackedSA(mlp_module)
 
 
 def fold_fp_mlp(mlp_module):
     return [pt_utils.fold_conv_bn(block) for block in mlp_module]
 
 
-def sa_forward(xyz, new_xyz, features, radius, nsample, normalize_xyz, folded):
-    raise RuntimeError("fused SA kernel not built")
+def point_major(features):
+    """(B,C,N) channel-major features -> a (B,N,C)-indexable fp32 view with unit channel stride.
+    Layers that produced `features` attach the point-major twin they already have
+    (`_bqa_pm`), so no transpose kernel runs between fused layers."""
+    pm = getattr(features, "_bqa_pm", None)
+    if (pm is not None and pm.dtype == _f32 and pm.device == features.device and pm.dim() == 3
+            and pm.size(0) == features.size(0) and pm.size(1) == features.size(2)
+            and pm.size(2) == features.size(1) and pm.stride(2) == 1
+            and pm.stride(0) == pm.size(1) * pm.stride(1)):
+        return pm
+    return _ext.transpose_to_point_major(features.contiguous())
+
+
+def sa_forward(xyz, new_xyz, features, radius, nsample, normalize_xyz, packed):
+    """-> new_features (B, C3, npoint) fp32, with a point-major twin attached as ._bqa_pm."""
+    N.check_tensor(xyz, "xyz", _f32)
+    N.check_tensor(new_xyz, "new_xyz", _f32)
+    b, n, _ = xyz.shape
+    npoint = new_xyz.size(1)
+    idx = _ext.ball_query(new_xyz, xyz, radius, nsample)
+    if features is not None:
+        pm = point_major(features)
+        c, stride = pm.size(2), pm.stride(1)
+    else:
+        pm, c, stride = None, 0, 0
+    out_cm = torch.empty((b, packed.c3, npoint), dtype=_f32, device=xyz.device)
+    out_pm = torch.empty((b, npoint, packed.c3), dtype=_f32, device=xyz.device)
+    with torch.cuda.device(xyz.device):
+        N.call("bqa_sa_mlp_max_forward", b, n, npoint, int(nsample), c, N.ptr(xyz), N.ptr(new_xyz),
+               N.ptr(pm), stride, N.ptr(idx), ctypes.c_float(radius), 1 if normalize_xyz else 0,
+               packed.c1, packed.c2, packed.c3,
+               N.ptr(packed.packed[0]), N.ptr(packed.bias[0]), N.ptr(packed.packed[1]),
+               N.ptr(packed.bias[1]), N.ptr(packed.packed[2]), N.ptr(packed.bias[2]),
+               N.ptr(out_cm), N.ptr(out_pm), N.stream_ptr(xyz.device))
+    out_cm._bqa_pm = out_pm
+    return out_cm
 
 
 def fp_forward(unknown, known, unknow_feats, known_feats, folded):

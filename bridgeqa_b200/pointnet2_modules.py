@@ -136,7 +136,7 @@ class PointnetSAModuleVotes(nn.Module):
         return (fused.enabled() and self.npoint is not None and self.pooling == 'max'
                 and self.use_xyz and not self.sample_uniformly and not self.training
                 and not torch.is_grad_enabled() and xyz.is_cuda
-                and fused.sa_supported(self.mlp_module, self.nsample,
+                and fused.sa_supported(self.mlp_module, self.nsample, self.npoint,
                                        0 if features is None else features.size(1)))
 
     def train(self, mode=True):
@@ -152,10 +152,11 @@ class PointnetSAModuleVotes(nn.Module):
             new_xyz = None
 
         if self._can_fuse(xyz, features):
-            if self._fused_cache is None:
-                self._fused_cache = fused.fold_sa_mlp(self.mlp_module)
+            sig = fused.weights_signature(self.mlp_module)
+            if self._fused_cache is None or self._fused_cache[0] != sig:
+                self._fused_cache = (sig, fused.fold_sa_mlp(self.mlp_module))
             new_features = fused.sa_forward(xyz, new_xyz, features, self.radius, self.nsample,
-                                            self.normalize_xyz, self._fused_cache)
+                                            self.normalize_xyz, self._fused_cache[1])
             return new_xyz, new_features, inds
 
         grouped = self.grouper(xyz, new_xyz, features)

@@ -94,6 +94,39 @@ BQA_API int bqa_three_interpolate_grad(int b, int c, int n, int m, const float *
                                const int *idx, const float *weight, float *grad_points,
                                void *stream);
 
+/* ---- fused set-abstraction layer (inference; eval-mode BN folded into W/bias) ---------
+ * replaces the chain  QueryAndGroup.forward (pointnet2_utils.py:317-376: group xyz,
+ * subtract centre, divide by radius, group features, concat) -> SharedMLP of three
+ * [1x1 conv -> BN -> ReLU] blocks (pytorch_utils.py:11-36) -> max_pool2d over nsample
+ * (pointnet2_modules.py:259-262), without materialising the grouped tensor or any
+ * activation in HBM.  bf16 operands, fp32 accumulation on tcgen05 tensor cores.
+ *
+ * bqa_pack_weight_bf16: w (c_out, c_in) f32 row-major (BN already folded) -> the bf16
+ *   shared-memory image the kernel loads, [k_pad/8][c_out][8], k_pad a multiple of 16,
+ *   zero padded.  xyz_first=1: source columns are [xyz(3), feat(c_in-3)] (torch.cat order
+ *   at pointnet2_utils.py:357) and are re-ordered to [feat, xyz] to match the kernel's
+ *   gather.  `packed` needs 2*c_out*k_pad bytes.
+ * bqa_sa_mlp_max_supported: 1 if the shape is handled (nsample in {16,32,64,128},
+ *   npoint*nsample a multiple of 128, mlp widths (64,64,128) | (128,128,256) | (128,128,128)).
+ * bqa_sa_mlp_max_forward: xyz (b,n,3) f32; new_xyz (b,npoint,3) f32; feat_pm (b,n,c)
+ *   POINT-MAJOR f32 (NULL iff c == 0) whose consecutive points are feat_stride floats apart
+ *   (feat_stride >= c; scenes are n*feat_stride apart -- lets SA1 read the features straight
+ *   out of the (b,n,3+c) input cloud); idx (b,npoint,nsample) i32 from bqa_ball_query;
+ *   w{1,2,3}p packed with k_pad = roundup16(c+3), c1, c2; b{1,2,3} f32 biases.
+ *   grouped xyz is (xyz[idx] - new_xyz) and, when normalize_xyz, divided by `radius`.
+ *   out_cm (b,c3,npoint) f32 = the reference's new_features; out_pm (b,npoint,c3) f32
+ *   optional point-major copy for the next layer (NULL to skip). */
+BQA_API int bqa_pack_weight_bf16(int c_out, int c_in, int k_pad, int xyz_first, const float *w,
+                                 void *packed, void *stream);
+BQA_API int bqa_sa_mlp_max_supported(int nsample, int npoint, int c, int c1, int c2, int c3);
+BQA_API int bqa_sa_mlp_max_forward(int b, int n, int npoint, int nsample, int c, const float *xyz,
+                                   const float *new_xyz, const float *feat_pm, int feat_stride,
+                                   const int *idx,
+                                   float radius, int normalize_xyz, int c1, int c2, int c3,
+                                   const void *w1p, const float *b1, const void *w2p,
+                                   const float *b2, const void *w3p, const float *b3,
+                                   float *out_cm, float *out_pm, void *stream);
+
 /* ---- layout helper -------------------------------------------------------------
  * (b,c,n) channel-major -> (b,n,c) point-major, the layout the fused SA kernel gathers
  * from (one contiguous row per neighbour).  Replaces nothing in the reference; it is
