@@ -178,7 +178,8 @@ def algorithmic_work(name, dims):
         b, c, n = dims[:3]
         return {"bytes": 8 * b * c * n, "bound": "hbm"}
     if name == "bqa_sa_mlp_max_forward":
-        b, n, npt, ns, c, c1, c2, c3 = dims[:8]
+        b, n, npt, ns, c = dims[:5]
+        c1, c2, c3 = dims[7:10]          # dims[5:7] = feat_stride, normalize_xyz
         flops = 2 * b * npt * ns * ((c + 3) * c1 + c1 * c2 + c2 * c3)
         byts = b * (4 * npt * ns + 4 * npt * ns * (c + 3) + 4 * c3 * npt)
         return {"bytes": byts, "flops": flops, "bound": "tensor"}

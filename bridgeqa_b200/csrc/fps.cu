@@ -28,12 +28,11 @@ namespace bqa {
 
 namespace {
 
-constexpr int kThreads = 512;
-constexpr int kWarps = kThreads / 32;
 constexpr int kMaxCluster = 16;
 constexpr unsigned kFull = 0xffffffffu;
 
-struct __align__(16) Candidate {  // what one CTA tells the cluster about its winner
+// What one CTA tells the cluster about its winner (32-byte slot, two 16-byte halves).
+struct __align__(16) Candidate {
   uint32_t valbits;               // 0 = "no selectable point", else float bits + 1
   uint32_t nkey;                  // ~tie_key: larger is better
   float x, y;
@@ -62,27 +61,64 @@ __device__ __forceinline__ void warp_argmax(uint32_t &vb, uint32_t &nk) {
   nk = l;
 }
 
-template <int P>
-__global__ void __launch_bounds__(kThreads, 1)
-fps_cluster_kernel(int n, int m, int cs, int bits, const float *__restrict__ xyz_all,
-                   int *__restrict__ idx_all, float *__restrict__ new_xyz_all) {
+#ifdef BQA_FPS_TRACE
+}  // namespace
+unsigned long long *g_fps_trace = nullptr;
+namespace {
+#define FPS_TRACE_ARG , unsigned long long *trace
+#define FPS_TRACE_PASS , g_fps_trace
+#define FPS_TRACE_BEGIN const bool tr = trace && blockIdx.x == 0 && threadIdx.x == 0; long long tc = clock64(), tl0 = tc;
+#define FPS_TRACE(i) if (tr) { long long now = clock64(); trace[i] += (unsigned long long)(now - tc); tc = now; }
+#define FPS_TRACE_TOTAL(i) if (tr) { long long now = clock64(); trace[i] += (unsigned long long)(now - tl0); tl0 = now; tc = now; }
+#else
+#define FPS_TRACE_ARG
+#define FPS_TRACE_PASS
+#define FPS_TRACE_BEGIN
+#define FPS_TRACE(i)
+#define FPS_TRACE_TOTAL(i)
+#endif
+
+// P points per thread, T threads per CTA, cs CTAs per scene (runtime; cs_magic =
+// ceil(2^32 / cs) so that q / cs == __umulhi(q, cs_magic) for the small q used here).
+//
+// One iteration, in dependent-latency order (cycle counts measured on B200 with
+// tools/fps_trace.cu and tools/ubench.cu):
+//   1. every thread updates its P min-distances (6 FMA-pipe ops per point: the floor of
+//      this kernel is P * 6 * warps-per-scheduler cycles) and keeps (value, slot) of its max;
+//   2. warp argmax = two redux.sync (~28 cycles each); lane 0 posts (value, key);
+//   3. one __syncthreads; the 16 posts are folded with two more redux.sync -- by warp 0 only
+//      when the scene spans a cluster, by every warp (no second barrier) when it does not;
+//      the winner's coordinates come from the CTA's shared-memory copy of its points;
+//   4. cluster: warp 0 pushes (value, key, x, y, z) into every CTA of the cluster with
+//      st.async (complete_tx on the receiver's mbarrier, ~340 cycles one way, no cluster
+//      barrier); every warp folds the cs candidates that landed in its own shared memory.
+// Variants that were measured and lost: packed fp32x2 math for step 1 (FFMA2 issues at half
+// rate: 43 vs 22 cycles per point), one warp folding all 512 thread candidates from shared
+// memory (574 cycles), handing results over through shared memory instead of redux/shfl.
+template <int P, int T>
+__global__ void __launch_bounds__(T, 1)
+fps_cluster_kernel(int n, int m, int cs, uint32_t cs_magic, int bits,
+                   const float *__restrict__ xyz_all, int *__restrict__ idx_all,
+                   float *__restrict__ new_xyz_all FPS_TRACE_ARG) {
+  static_assert(T == 512, "slot <-> index arithmetic below assumes 512 threads (= max bs)");
+  constexpr int NW = T / 32;
+  constexpr int kLogT = 9;
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  // [ Candidate recv[2][kMaxCluster] | uint2 part[kWarps] | uint64 bar[2] | float4 bcast | sx,sy,sz ]
+  // [ Candidate recv[2][kMaxCluster] | uint2 part[2][NW] | u64 bar[2] | sx,sy,sz ]
   Candidate *recv = reinterpret_cast<Candidate *>(smem_raw);
   uint2 *part = reinterpret_cast<uint2 *>(recv + 2 * kMaxCluster);
-  uint64_t *bars = reinterpret_cast<uint64_t *>(part + kWarps);
-  float4 *bcast = reinterpret_cast<float4 *>(bars + 2);
-  float *sx = reinterpret_cast<float *>(bcast + 1);
-  float *sy = sx + P * kThreads;
-  float *sz = sy + P * kThreads;
+  uint64_t *bars = reinterpret_cast<uint64_t *>(part + 2 * NW);
+  float *sx = reinterpret_cast<float *>(bars + 2);
+  float *sy = sx + P * T;
+  float *sz = sy + P * T;
 
   const int tid = threadIdx.x;
   const int lane = tid & 31;
   const int wid = tid >> 5;
   const uint32_t rank = cs > 1 ? cluster_ctarank() : 0u;
   const int scene = blockIdx.x / cs;
-  const int t_total = cs * kThreads;
-  const int g = rank * kThreads + tid;  // this thread's slot in the scene-wide thread grid
+  const int t_total = cs * T;
+  const int g = rank * T + tid;  // this thread's slot in the scene-wide thread grid
 
   const float *xyz = xyz_all + (size_t)scene * n * 3;
   int *idxs = idx_all + (size_t)scene * m;
@@ -103,10 +139,13 @@ fps_cluster_kernel(int n, int m, int cs, int bits, const float *__restrict__ xyz
       if (!((double)mag <= 1e-3)) t = 1e10f;  // sampling_gpu.cu:100-101, sampling.cpp:74-76
     }
     px[p] = x; py[p] = y; pz[p] = z; td[p] = t;
-    sx[p * kThreads + tid] = x;
-    sy[p * kThreads + tid] = y;
-    sz[p * kThreads + tid] = z;
+    sx[p * T + tid] = x;
+    sy[p * T + tid] = y;
+    sz[p * T + tid] = z;
   }
+  // tie key of slot p is key0 + p * kstep (t_total is a multiple of bs = 1 << bits)
+  const uint32_t key0 = tie_key((uint32_t)g, bits);
+  const uint32_t kstep = (uint32_t)t_total >> bits;
 
   const uint32_t bar0 = smem_u32(&bars[0]);
   if (cs > 1) {
@@ -126,7 +165,10 @@ fps_cluster_kernel(int n, int m, int cs, int bits, const float *__restrict__ xyz
     if (new_xyz) { new_xyz[0] = x1; new_xyz[1] = y1; new_xyz[2] = z1; }
   }
 
+  FPS_TRACE_BEGIN
   for (int j = 1; j < m; ++j) {
+    const int buf = j & 1;
+    // ---- 1. update the P running min-distances, keep the thread's max --------------------
     float best = -1.f;
     int bslot = 0;
 #pragma unroll
@@ -137,27 +179,33 @@ fps_cluster_kernel(int n, int m, int cs, int bits, const float *__restrict__ xyz
       td[p] = d2;
       if (d2 > best) { best = d2; bslot = p; }   // strict: lowest k wins inside a thread
     }
-    uint32_t vb = 0u, nk = 0xffffffffu;          // "nothing selectable" decodes to k = 0
-    if (best >= 0.f) {
-      vb = __float_as_uint(best) + 1u;
-      nk = ~tie_key((uint32_t)(bslot * t_total + g), bits);
-    }
+    const bool valid = best >= 0.f;
+    uint32_t vb = valid ? __float_as_uint(best) + 1u : 0u;
+    uint32_t nk = valid ? ~(key0 + (uint32_t)bslot * kstep) : 0xffffffffu;   // invalid decodes to k = 0
+    // ---- 2. warp argmax -> post --------------------------------------------------------
     warp_argmax(vb, nk);
-    if (lane == 0) part[wid] = make_uint2(vb, nk);
+    if (lane == 0) part[buf * NW + wid] = make_uint2(vb, nk);
+    FPS_TRACE(0)
     __syncthreads();
-
-    if (wid == 0) {
-      uint2 c = lane < kWarps ? part[lane] : make_uint2(0u, 0u);
+    FPS_TRACE(1)
+    uint32_t old;
+    if (cs == 1) {
+      // ---- 3. every warp folds the NW posts; slot index == point index when cs == 1 ------
+      uint2 c = lane < NW ? part[buf * NW + lane] : make_uint2(0u, 0u);
       warp_argmax(c.x, c.y);
-      const uint32_t k = key_to_index(~c.y, bits);
-      // this CTA's winner is one of its own points (or k = 0 when it has none)
-      const int loc = (int)(k / (uint32_t)t_total) * kThreads + (int)(k % (uint32_t)kThreads);
-      const float wx = sx[loc], wy = sy[loc], wz = sz[loc];
-      if (cs == 1) {
-        if (lane == 0) *bcast = make_float4(wx, wy, wz, __uint_as_float(k));
-      } else {
-        const int jj = j - 1;
-        const uint32_t bar = bar0 + 8u * (jj & 1);
+      old = key_to_index(~c.y, bits);
+      x1 = sx[old]; y1 = sy[old]; z1 = sz[old];
+      FPS_TRACE(2)
+    } else {
+      const int jj = j - 1;
+      const uint32_t bar = bar0 + 8u * (jj & 1);
+      if (wid == 0) {
+        // ---- 3. warp 0 folds the posts and 4a. pushes the CTA's candidate to every peer ---
+        uint2 c = lane < NW ? part[buf * NW + lane] : make_uint2(0u, 0u);
+        warp_argmax(c.x, c.y);
+        const uint32_t key = ~c.y;                       // (bitrev(tid) << 22) | (p * cs + rank)
+        const int loc = (int)__umulhi(key & 0x3fffffu, cs_magic) * T + (int)(__brev(key >> 22) >> 23);
+        const float wx = sx[loc], wy = sy[loc], wz = sz[loc];   // own point, or slot 0 if none
         const uint32_t slot = smem_u32(&recv[(jj & 1) * kMaxCluster + rank]);
         if (lane == 0) mbar_arrive_expect_tx(bar, 20u * cs);
         if (lane < cs) {
@@ -168,35 +216,26 @@ fps_cluster_kernel(int n, int m, int cs, int bits, const float *__restrict__ xyz
                        mapa_shared(bar, lane - cs));
         }
       }
+      FPS_TRACE(2)
+      // ---- 4b. fold the cs candidates that landed in this CTA (every warp, no barrier) ----
+      mbar_wait(bar, (jj >> 1) & 1);
+      FPS_TRACE(3)
+      const Candidate *rb = &recv[(jj & 1) * kMaxCluster];
+      uint2 gc = make_uint2(0u, 0u);
+      if (lane < cs) gc = *reinterpret_cast<const uint2 *>(&rb[lane]);
+      warp_argmax(gc.x, gc.y);
+      // owner CTA of the winner: key & 0x3fffff = k >> 9 = p * cs + rank (bs is 512 whenever a
+      // scene spans a cluster); all-invalid decodes to k = 0, owned by rank 0
+      const uint32_t q = ~gc.y & 0x3fffffu;
+      const uint32_t owner = q - __umulhi(q, cs_magic) * (uint32_t)cs;
+      const float2 xy = *reinterpret_cast<const float2 *>(&rb[owner].x);
+      x1 = xy.x; y1 = xy.y; z1 = rb[owner].z;
+      old = gc.y;                                        // decoded off the critical path
+      FPS_TRACE(4)
     }
-
-    uint32_t old;
-    if (cs == 1) {
-      __syncthreads();
-      const float4 w = *bcast;
-      x1 = w.x; y1 = w.y; z1 = w.z; old = __float_as_uint(w.w);
-    } else {
-      const int jj = j - 1;
-      mbar_wait(bar0 + 8u * (jj & 1), (jj >> 1) & 1);
-      uint32_t cv = 0u, ck = 0u;
-      float cx = 0.f, cy = 0.f, cz = 0.f;
-      if (lane < cs) {
-        const Candidate *c = &recv[(jj & 1) * kMaxCluster + lane];
-        const uint4 q = *reinterpret_cast<const uint4 *>(c);
-        cv = q.x; ck = q.y; cx = __uint_as_float(q.z); cy = __uint_as_float(q.w);
-        cz = c->z;
-      }
-      uint32_t mv = cv, mk = ck;
-      warp_argmax(mv, mk);
-      // all-invalid: every CTA reports (0, ~0) and the lowest rank (owner of k=0) wins
-      const int src = __ffs(__ballot_sync(kFull, lane < cs && cv == mv && ck == mk)) - 1;
-      x1 = __shfl_sync(kFull, cx, src);
-      y1 = __shfl_sync(kFull, cy, src);
-      z1 = __shfl_sync(kFull, cz, src);
-      old = key_to_index(~mk, bits);
-    }
+    FPS_TRACE_TOTAL(5)
     if (rank == 0 && tid == 0) {
-      idxs[j] = (int)old;  // sampling_gpu.cu:170-171
+      idxs[j] = (int)(cs == 1 ? old : key_to_index(~old, bits));   // sampling_gpu.cu:170-171
       if (new_xyz) { new_xyz[j * 3 + 0] = x1; new_xyz[j * 3 + 1] = y1; new_xyz[j * 3 + 2] = z1; }
     }
   }
@@ -262,61 +301,119 @@ fps_global_kernel(int n, int m, int bits, const float *__restrict__ xyz_all,
   }
 }
 
+constexpr int kT = 512;     // threads per CTA of the register-resident kernel
+constexpr int kMaxP = 20;   // points per thread: 4 registers each, 128 registers per thread at 512 threads
+
 template <int P>
 size_t fps_smem_bytes() {
-  return sizeof(Candidate) * 2 * kMaxCluster + sizeof(uint2) * kWarps + 16 + 16 +
-         sizeof(float) * 3 * P * kThreads;
+  return sizeof(Candidate) * 2 * kMaxCluster + sizeof(uint2) * 2 * (kT / 32) + 16 +
+         sizeof(float) * 3 * P * kT;
+}
+
+template <int P>
+cudaError_t fps_config(cudaLaunchConfig_t *cfg, cudaLaunchAttribute *attr, int b, int cs,
+                       cudaStream_t stream) {
+  const size_t smem = fps_smem_bytes<P>();
+  cudaError_t e = cudaFuncSetAttribute(fps_cluster_kernel<P, kT>,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  if (cs > 8) {
+    e = cudaFuncSetAttribute(fps_cluster_kernel<P, kT>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+    if (e != cudaSuccess) return e;
+  }
+  *cfg = cudaLaunchConfig_t{};
+  cfg->gridDim = dim3((unsigned)(b * cs));
+  cfg->blockDim = dim3(kT);
+  cfg->dynamicSmemBytes = smem;
+  cfg->stream = stream;
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = (unsigned)cs;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg->attrs = attr;
+  cfg->numAttrs = 1;
+  return cudaSuccess;
 }
 
 template <int P>
 int launch_fps(int b, int n, int m, int cs, int bits, const float *xyz, int *idxs, float *new_xyz,
                cudaStream_t stream) {
-  const size_t smem = fps_smem_bytes<P>();
-  BQA_CUDA(cudaFuncSetAttribute(fps_cluster_kernel<P>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                (int)smem));
-  if (cs > 8)
-    BQA_CUDA(cudaFuncSetAttribute(fps_cluster_kernel<P>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
-  cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3((unsigned)(b * cs));
-  cfg.blockDim = dim3(kThreads);
-  cfg.dynamicSmemBytes = smem;
-  cfg.stream = stream;
+  cudaLaunchConfig_t cfg;
   cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = (unsigned)cs;
-  attr[0].val.clusterDim.y = 1;
-  attr[0].val.clusterDim.z = 1;
-  cfg.attrs = attr;
-  cfg.numAttrs = 1;
-  BQA_CUDA(cudaLaunchKernelEx(&cfg, fps_cluster_kernel<P>, n, m, cs, bits, xyz, idxs, new_xyz));
+  BQA_CUDA(fps_config<P>(&cfg, attr, b, cs, stream));
+  const uint32_t cs_magic = (uint32_t)((0x100000000ull + (unsigned)cs - 1) / (unsigned)cs);
+  BQA_CUDA(cudaLaunchKernelEx(&cfg, fps_cluster_kernel<P, kT>, n, m, cs, cs_magic, bits, xyz, idxs,
+                              new_xyz FPS_TRACE_PASS));
   count_launch();
   return check_launch("fps_cluster_kernel");
 }
 
+template <int P>
+int max_clusters(int cs) {
+  cudaLaunchConfig_t cfg;
+  cudaLaunchAttribute attr[1];
+  if (fps_config<P>(&cfg, attr, 1, cs, 0) != cudaSuccess) { cudaGetLastError(); return 0; }
+  int ncl = 0;
+  if (cudaOccupancyMaxActiveClusters(&ncl, fps_cluster_kernel<P, kT>, &cfg) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  return ncl;
+}
+
+#define BQA_FPS_DISPATCH(per_thread, EXPR)            \
+  do {                                                \
+    if ((per_thread) <= 1) { constexpr int PP_ = 1; EXPR; }        \
+    else if ((per_thread) <= 2) { constexpr int PP_ = 2; EXPR; }   \
+    else if ((per_thread) <= 4) { constexpr int PP_ = 4; EXPR; }   \
+    else if ((per_thread) <= 6) { constexpr int PP_ = 6; EXPR; }   \
+    else if ((per_thread) <= 8) { constexpr int PP_ = 8; EXPR; }   \
+    else if ((per_thread) <= 10) { constexpr int PP_ = 10; EXPR; } \
+    else if ((per_thread) <= 12) { constexpr int PP_ = 12; EXPR; } \
+    else if ((per_thread) <= 14) { constexpr int PP_ = 14; EXPR; } \
+    else if ((per_thread) <= 16) { constexpr int PP_ = 16; EXPR; } \
+    else { constexpr int PP_ = 20; EXPR; }                         \
+  } while (0)
+
 }  // namespace
 
-// Largest per-thread point count instantiated.
-static const int kMaxP = 16;
-
-static void fps_plan(int n, int *cs_out, int *per_thread_out) {
-  // smallest cluster whose threads hold the scene with <= 10 points each (more CTAs per
-  // scene shorten the per-iteration update, but the hop across the cluster costs
-  // latency, so small scenes stay in one CTA); 16-CTA clusters are non-portable and only
-  // used when 8 CTAs x 16 points cannot hold the scene.
-  int cs = 1;
-  if (n > kThreads * kMaxP) {
-    cs = 2;
-    while (cs < 8 && (long long)cs * kThreads * 10 < n) cs *= 2;
-    if ((long long)cs * kThreads * kMaxP < n) cs = 16;
+// How many CTAs share one scene.  A scene must fit in the registers of its cluster
+// (cs * 512 threads * <= 20 points); among the sizes that fit, pick the one with the lowest
+// modelled time  waves * (fixed + per-point work / cs)  where waves = ceil(b / clusters that
+// are co-resident on this GPU) -- measured on B200: 8-CTA clusters co-reside 15 at a time,
+// 6-CTA 22, 4-CTA 33, so 16 scenes of 40k points run best on 6-CTA clusters.
+static void fps_plan(int b, int n, int *cs_out, int *per_thread_out) {
+  static int cached_clusters[17] = {0};
+  static const int kSizes[] = {1, 2, 4, 6, 8, 16};
+  int best_cs = 0;
+  double best_t = 0;
+  for (int cs : kSizes) {
+    const int per_thread = ceil_div(n, cs * kT);
+    if (per_thread > kMaxP) continue;
+    int ncl;
+    if (cs == 1) {
+      ncl = 1 << 20;
+    } else {
+      if (!cached_clusters[cs]) {
+        int v = 0;
+        BQA_FPS_DISPATCH(kMaxP, v = max_clusters<PP_>(cs));   // worst-case shared memory
+        cached_clusters[cs] = v > 0 ? v : -1;
+      }
+      ncl = cached_clusters[cs];
+      if (ncl <= 0) continue;
+    }
+    const int waves = ceil_div(b, ncl);
+    // cycles per iteration: ~800 fixed (+350 for the cluster hop) + ~0.06 per point per CTA
+    const double t = waves * ((cs == 1 ? 600.0 : 1000.0) + 0.06 * (double)n / cs);
+    if (!best_cs || t < best_t) { best_cs = cs; best_t = t; }
   }
-  *cs_out = cs;
-  *per_thread_out = ceil_div(n, cs * kThreads);
+  *cs_out = best_cs;
+  *per_thread_out = best_cs ? ceil_div(n, best_cs * kT) : kMaxP + 1;
 }
 
 long long fps_scratch_bytes(int b, int n) {
-  int cs, per_thread;
-  fps_plan(n, &cs, &per_thread);
-  return per_thread > kMaxP ? (long long)sizeof(float) * b * n : 0;
+  // conservative: scenes beyond what a 16-CTA cluster holds need the global-memory variant
+  return (long long)n > 16ll * kT * kMaxP ? (long long)sizeof(float) * b * n : 0;
 }
 
 int fps_dispatch(int b, int n, int m, const float *xyz, int *idxs, float *new_xyz, float *scratch,
@@ -327,30 +424,19 @@ int fps_dispatch(int b, int n, int m, const float *xyz, int *idxs, float *new_xy
   if ((long long)n >= (1ll << 22) * bs) return set_error(BQA_ERR_UNSUPPORTED, "fps: n=%d too large", n);
 
   int cs, per_thread;
-  fps_plan(n, &cs, &per_thread);
+  fps_plan(b, n, &cs, &per_thread);
   if (per_thread > kMaxP) {
     if (!scratch)
       return set_error(BQA_ERR_INVALID_ARG,
-                       "fps: n=%d needs bqa_fps_scratch_bytes() = %lld bytes of scratch", n,
-                       fps_scratch_bytes(b, n));
+                       "fps: n=%d needs %lld bytes of scratch (see bqa_fps_scratch_bytes)", n,
+                       (long long)sizeof(float) * b * n);
     fps_global_kernel<<<b, 1024, 0, stream>>>(n, m, bits, xyz, scratch, idxs, new_xyz);
     count_launch();
     return check_launch("fps_global_kernel");
   }
-#define BQA_FPS_CASE(PP) \
-  if (per_thread <= PP) return launch_fps<PP>(b, n, m, cs, bits, xyz, idxs, new_xyz, stream);
-  BQA_FPS_CASE(1)
-  BQA_FPS_CASE(2)
-  BQA_FPS_CASE(3)
-  BQA_FPS_CASE(4)
-  BQA_FPS_CASE(5)
-  BQA_FPS_CASE(6)
-  BQA_FPS_CASE(8)
-  BQA_FPS_CASE(10)
-  BQA_FPS_CASE(12)
-  BQA_FPS_CASE(16)
-#undef BQA_FPS_CASE
-  return set_error(BQA_ERR_UNSUPPORTED, "fps: internal dispatch error");
+  int rc = BQA_ERR_UNSUPPORTED;
+  BQA_FPS_DISPATCH(per_thread, rc = launch_fps<PP_>(b, n, m, cs, bits, xyz, idxs, new_xyz, stream));
+  return rc;
 }
 
 }  // namespace bqa
