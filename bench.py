@@ -46,9 +46,11 @@ def measured_peaks():
 # --------------------------------------------------------------------------- clocks ---
 
 class ClockSampler(object):
-    """nvidia-smi sampled every 200 ms DURING the timed region (B200_PROFILING.md recipe)."""
+    """nvidia-smi sampled every 20 ms; started before warm-up (the tool takes ~0.5 s to come
+    up), reported over the samples taken between mark_begin() and mark_end(), i.e. DURING the
+    timed region (B200_PROFILING.md recipe)."""
 
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+    Q = ("timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
@@ -56,6 +58,13 @@ class ClockSampler(object):
         self.proc = None
         self.path = None
         self.index = index
+        self.t_begin = self.t_end = None
+
+    def mark_begin(self):
+        self.t_begin = time.time()
+
+    def mark_end(self):
+        self.t_end = time.time()
 
     def start(self):
         try:
@@ -63,7 +72,7 @@ class ClockSampler(object):
             os.close(fd)
             self.proc = subprocess.Popen(
                 ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                 "--format=csv,noheader,nounits", "-lms", "200"],
+                 "--format=csv,noheader,nounits", "-lms", "20"],
                 stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
         except Exception:
             self.proc = None
@@ -78,16 +87,23 @@ class ClockSampler(object):
         except Exception:
             self.proc.kill()
         sm, mx, reasons = [], [], set()
+        import datetime
         try:
+            rows = []
             for line in open(self.path):
                 f = [x.strip() for x in line.split(",")]
                 if len(f) < 8:
                     continue
                 try:
-                    sm.append(float(f[1]))
-                    mx.append(float(f[2]))
+                    ts = datetime.datetime.strptime(f[0], "%Y/%m/%d %H:%M:%S.%f").timestamp()
+                    rows.append((ts, float(f[1]), float(f[2]), f))
                 except ValueError:
                     continue
+            inside = [r for r in rows if self.t_begin is not None and self.t_begin - 0.02 <= r[0] <= self.t_end + 0.02]
+            out["window"] = "timed region" if inside else "whole run (timed region shorter than one sample)"
+            for ts, a, b_, f in (inside or rows):
+                sm.append(a)
+                mx.append(b_)
                 for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown",
                                     "sw_power_cap"), f[4:8]):
                     if v.lower().startswith("active"):
@@ -194,12 +210,14 @@ def algorithmic_work(name, dims):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--unfused", action="store_true", help="force the un-fused operator path")
     ap.add_argument("--tf32", action="store_true", help="allow TF32 in torch convs of the un-fused path")
+    ap.add_argument("--precision", default="fp16", choices=["fp16", "bf16"],
+                    help="operand format of the fused tensor-core kernels (fp32 accumulate)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference_arm(args)
@@ -221,6 +239,7 @@ def main():
     args.warmup = max(args.warmup, 3)
     if args.unfused:
         bridgeqa_b200.set_fused(False)
+    bridgeqa_b200.set_precision(args.precision)
     torch.backends.cudnn.allow_tf32 = bool(args.tf32)
     torch.backends.cuda.matmul.allow_tf32 = bool(args.tf32)
 
@@ -246,14 +265,15 @@ def main():
             dist.barrier()
             torch.cuda.synchronize()
 
+    clocks = ClockSampler(local_rank)
+    if rank == 0:
+        clocks.start()
     for i in range(args.warmup):
         step(i)
     barrier()
 
     # ---- timed region: exactly K steps, device-timed, per-kernel events recorded live ----
-    clocks = ClockSampler(local_rank)
-    if rank == 0:
-        clocks.start()
+    clocks.mark_begin()
     launches0 = _native.launch_count()
     ev0 = torch.cuda.Event(enable_timing=True)
     ev1 = torch.cuda.Event(enable_timing=True)
@@ -263,6 +283,7 @@ def main():
             step(i)
         ev1.record()
         barrier()
+    clocks.mark_end()
     elapsed_ms = ev0.elapsed_time(ev1)
     launches = _native.launch_count() - launches0
     clk = clocks.stop() if rank == 0 else None
@@ -341,7 +362,8 @@ def main():
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None,
-            "dtype": "bf16" if any(r["kernel"] == "bqa_sa_mlp_max_forward" for r in kernels) else "f32",
+            "dtype": ("f16" if bridgeqa_b200.fused.precision() == "fp16" else "bf16")
+                     if any(r["kernel"] == "bqa_sa_mlp_max_forward" for r in kernels) else "f32",
             "data": "synthetic",
             "config": {"workload": WORKLOAD, "global_batch": BATCH * world, "num_points": NUM_POINTS,
                        "parallelism": "scenes sharded by batch index, %d/GPU, no collective in forward" % BATCH,

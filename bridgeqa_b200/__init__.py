@@ -11,6 +11,6 @@ Public surface (mirrors /root/reference/lib/pointnet2 and the three model files 
 
 There is no CPU / eager fallback: every operator goes through libbqa_pointnet2.so.
 """
-from .fused import set_fused  # noqa: F401
+from .fused import set_fused, set_precision  # noqa: F401
 
 __version__ = "0.1.0"

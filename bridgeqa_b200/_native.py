@@ -28,17 +28,18 @@ _SIGNATURES = {
     "bqa_furthest_point_sampling": ([_I, _I, _I, _P, _P, _P, _P, _P], _I),
     "bqa_gather_points": ([_I, _I, _I, _I, _P, _P, _P, _P], _I),
     "bqa_gather_points_grad": ([_I, _I, _I, _I, _P, _P, _P, _P], _I),
-    "bqa_ball_query": ([_I, _I, _I, _F, _I, _P, _P, _P, _P], _I),
+    "bqa_ball_query_workspace_bytes": ([_I, _I, _I, _I], _LL),
+    "bqa_ball_query": ([_I, _I, _I, _F, _I, _P, _P, _P, _P, _P], _I),
     "bqa_group_points": ([_I, _I, _I, _I, _I, _P, _P, _P, _P], _I),
     "bqa_group_points_grad": ([_I, _I, _I, _I, _I, _P, _P, _P, _P], _I),
     "bqa_three_nn": ([_I, _I, _I, _P, _P, _P, _P, _P], _I),
     "bqa_three_interpolate": ([_I, _I, _I, _I, _P, _P, _P, _P, _P], _I),
     "bqa_three_interpolate_grad": ([_I, _I, _I, _I, _P, _P, _P, _P, _P], _I),
     "bqa_transpose_to_point_major": ([_I, _I, _I, _P, _P, _P], _I),
-    "bqa_pack_weight_bf16": ([_I, _I, _I, _I, _P, _P, _P], _I),
+    "bqa_pack_weight_16": ([_I, _I, _I, _I, _I, _P, _P, _P], _I),
     "bqa_sa_mlp_max_supported": ([_I, _I, _I, _I, _I, _I], _I),
     "bqa_sa_mlp_max_forward": ([_I, _I, _I, _I, _I, _P, _P, _P, _I, _P, _F, _I, _I, _I, _I,
-                                _P, _P, _P, _P, _P, _P, _P, _P, _P], _I),
+                                _P, _P, _P, _P, _P, _P, _P, _P, _I, _P], _I),
 }
 
 _lib = None

@@ -44,7 +44,8 @@ int fps_dispatch(int b, int n, int m, const float *xyz, int *idxs, float *new_xy
                  cudaStream_t stream);
 long long fps_scratch_bytes(int b, int n);
 int ball_query_dispatch(int b, int n, int m, float radius, int nsample, const float *new_xyz,
-                        const float *xyz, int *idx, cudaStream_t stream);
+                        const float *xyz, int *idx, void *workspace, cudaStream_t stream);
+long long ball_query_workspace_bytes(int b, int n, int m, int nsample);
 int gather_rows_dispatch(int b, int c, int n, long long e_total, const float *points, const int *idx,
                          float *out, cudaStream_t stream);
 int scatter_add_rows_dispatch(int b, int c, int n, long long e_total, const float *grad_out,
@@ -58,13 +59,13 @@ int three_interpolate_grad_dispatch(int b, int c, int n, int m, const float *gra
                                     const float *weight, float *grad_points, cudaStream_t stream);
 
 int sa_supported(int nsample, int npoint, int c, int c1, int c2, int c3);
-int pack_weight_dispatch(int c_out, int c_in, int kpad, int xyz_first, const float *w, void *packed,
-                         cudaStream_t stream);
+int pack_weight_dispatch(int c_out, int c_in, int kpad, int xyz_first, int fp16, const float *w,
+                         void *packed, cudaStream_t stream);
 int sa_forward_dispatch(int b, int n, int npoint, int nsample, int c, const float *xyz,
                         const float *new_xyz, const float *feat_pm, int feat_stride, const int *idx, float radius,
                         int normalize_xyz, int c1, int c2, int c3, const void *w1p, const float *b1,
                         const void *w2p, const float *b2, const void *w3p, const float *b3,
-                        float *out_cm, float *out_pm, cudaStream_t stream);
+                        float *out_cm, float *out_pm, int fp16, cudaStream_t stream);
 
 }  // namespace bqa
 
@@ -107,13 +108,19 @@ int bqa_gather_points_grad(int b, int c, int n, int m, const float *grad_out, co
   return scatter_add_rows_dispatch(b, c, n, m, grad_out, idx, grad_points, (cudaStream_t)stream);
 }
 
+long long bqa_ball_query_workspace_bytes(int b, int n, int m, int nsample) {
+  if (b <= 0 || n <= 0 || m <= 0 || nsample <= 0) return 0;
+  return ball_query_workspace_bytes(b, n, m, nsample);
+}
+
 int bqa_ball_query(int b, int n, int m, float radius, int nsample, const float *new_xyz,
-                   const float *xyz, int *idx, void *stream) {
+                   const float *xyz, int *idx, void *workspace, void *stream) {
   NONNEG(b); NONNEG(n); NONNEG(m); NONNEG(nsample);
   if ((long long)b * m * nsample == 0) return BQA_OK;
   PTR(new_xyz); PTR(idx);
   if (n > 0) PTR(xyz);
-  return ball_query_dispatch(b, n, m, radius, nsample, new_xyz, xyz, idx, (cudaStream_t)stream);
+  return ball_query_dispatch(b, n, m, radius, nsample, new_xyz, xyz, idx, workspace,
+                             (cudaStream_t)stream);
 }
 
 int bqa_group_points(int b, int c, int n, int npoints, int nsample, const float *points,
@@ -169,14 +176,15 @@ int bqa_transpose_to_point_major(int b, int c, int n, const float *in, float *ou
   return transpose_cn_dispatch(b, c, n, in, out, (cudaStream_t)stream);
 }
 
-int bqa_pack_weight_bf16(int c_out, int c_in, int k_pad, int xyz_first, const float *w, void *packed,
-                         void *stream) {
+int bqa_pack_weight_16(int c_out, int c_in, int k_pad, int xyz_first, int precision, const float *w,
+                       void *packed, void *stream) {
+  BQA_REQUIRE(precision == 0 || precision == 1, "%s: precision must be 0 (bf16) or 1 (fp16)", __func__);
   BQA_REQUIRE(c_out > 0 && c_in > 0, "%s: empty weight", __func__);
   BQA_REQUIRE(k_pad >= c_in && k_pad % 16 == 0, "%s: k_pad=%d must be a multiple of 16 >= c_in=%d",
               __func__, k_pad, c_in);
   BQA_REQUIRE(!xyz_first || c_in >= 3, "%s: xyz_first needs c_in >= 3", __func__);
   PTR(w); PTR(packed);
-  return pack_weight_dispatch(c_out, c_in, k_pad, xyz_first, w, packed, (cudaStream_t)stream);
+  return pack_weight_dispatch(c_out, c_in, k_pad, xyz_first, precision, w, packed, (cudaStream_t)stream);
 }
 
 int bqa_sa_mlp_max_supported(int nsample, int npoint, int c, int c1, int c2, int c3) {
@@ -187,8 +195,9 @@ int bqa_sa_mlp_max_forward(int b, int n, int npoint, int nsample, int c, const f
                            const float *new_xyz, const float *feat_pm, int feat_stride, const int *idx, float radius,
                            int normalize_xyz, int c1, int c2, int c3, const void *w1p, const float *b1,
                            const void *w2p, const float *b2, const void *w3p, const float *b3,
-                           float *out_cm, float *out_pm, void *stream) {
+                           float *out_cm, float *out_pm, int precision, void *stream) {
   NONNEG(b); NONNEG(n); NONNEG(npoint); NONNEG(nsample); NONNEG(c);
+  BQA_REQUIRE(precision == 0 || precision == 1, "%s: precision must be 0 (bf16) or 1 (fp16)", __func__);
   if ((long long)b * npoint == 0) return BQA_OK;
   PTR(xyz); PTR(new_xyz); PTR(idx); PTR(w1p); PTR(b1); PTR(w2p); PTR(b2); PTR(w3p); PTR(b3); PTR(out_cm);
   BQA_REQUIRE((c == 0) == (feat_pm == nullptr), "%s: feat_pm must be NULL iff c == 0", __func__);
@@ -196,7 +205,7 @@ int bqa_sa_mlp_max_forward(int b, int n, int npoint, int nsample, int c, const f
   BQA_REQUIRE(!normalize_xyz || radius > 0.f, "%s: radius must be > 0", __func__);
   return sa_forward_dispatch(b, n, npoint, nsample, c, xyz, new_xyz, feat_pm, feat_stride, idx, radius,
                              normalize_xyz, c1, c2, c3, w1p, b1, w2p, b2, w3p, b3, out_cm, out_pm,
-                             (cudaStream_t)stream);
+                             precision, (cudaStream_t)stream);
 }
 
 }  // extern "C"

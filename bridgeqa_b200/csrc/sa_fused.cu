@@ -27,6 +27,7 @@
 // [features(C), xyz_rel(3), 0-pad] (the host packs W1 the same way) and processed in
 // chunks of 128 so that the weights of all three layers stay resident in shared memory.
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 
 #include "common.cuh"
 #include "tcgen05.cuh"
@@ -37,7 +38,15 @@ namespace {
 constexpr int kRows = 128;       // rows per tile == threads per CTA
 constexpr int kKChunk = 128;     // layer-1 K processed per pass
 
-__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+// two fp32 -> one packed 16-bit pair.  fp16 mode saturates at +-65504 instead of producing
+// inf (bf16 has fp32's range and needs no clamp).
+__device__ __forceinline__ uint32_t pack2(float lo, float hi, int fp16) {
+  if (fp16) {
+    lo = fminf(fmaxf(lo, -65504.f), 65504.f);
+    hi = fminf(fmaxf(hi, -65504.f), 65504.f);
+    __half2 v = __floats2half2_rn(lo, hi);
+    return *reinterpret_cast<uint32_t *>(&v);
+  }
   __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t *>(&v);
 }
@@ -51,6 +60,7 @@ struct SaParams {
   const int *idx;
   float radius;
   int normalize_xyz;
+  int fp16;                         // operands: 1 = fp16 (10-bit mantissa, saturating), 0 = bf16
   const uint4 *w1p, *w2p, *w3p;     // packed bf16 images [K/8][rows] of 16-byte vectors
   const float *b1, *b2, *b3;
   float *out_cm, *out_pm;
@@ -61,7 +71,7 @@ struct SaParams {
 // chunk-major ([CN/8][128] x 16 B) for the next MMA.
 template <int CN>
 __device__ __forceinline__ void epilogue_rows(uint32_t tmem_d, int warp, int row, const float *s_bias,
-                                              uint4 *x_buf) {
+                                              uint4 *x_buf, int fp16) {
 #pragma unroll
   for (int c0 = 0; c0 < CN; c0 += 32) {
     uint32_t v[32];
@@ -75,71 +85,82 @@ __device__ __forceinline__ void epilogue_rows(uint32_t tmem_d, int warp, int row
         const int col = c0 + q * 8 + e * 2;
         const float lo = fmaxf(__uint_as_float(v[q * 8 + e * 2]) + s_bias[col], 0.f);
         const float hi = fmaxf(__uint_as_float(v[q * 8 + e * 2 + 1]) + s_bias[col + 1], 0.f);
-        p[e] = pack_bf16x2(lo, hi);
+        p[e] = pack2(lo, hi, fp16);
       }
       x_buf[(c0 / 8 + q) * kRows + row] = make_uint4(p[0], p[1], p[2], p[3]);
     }
   }
 }
 
-template <int C1, int C2, int C3>
-__global__ void __launch_bounds__(kRows)
+// named barrier over the 128 threads of one tile pipeline (id 1 or 2; 0 is __syncthreads)
+__device__ __forceinline__ void group_sync(int group) {
+  asm volatile("bar.sync %0, 128;" ::"r"(group + 1) : "memory");
+}
+
+// Two independent tile pipelines per CTA (threads 0-127 and 128-255) share one copy of the
+// weights in shared memory; each has its own A/X buffer, mbarrier and TMEM columns, so the
+// gather / epilogue of one tile overlaps the MMAs of the other.
+template <int C1, int C2, int C3, int G>
+__global__ void __launch_bounds__(G * kRows)
 sa_mlp_max_kernel(const SaParams P) {
+  static_assert(G == 1 || G == 2, "one or two tile pipelines per CTA");
   static_assert(C1 % 32 == 0 && C2 % 32 == 0 && C3 % 128 == 0, "channel counts");
   constexpr int kXVecs = (C1 > C2 ? C1 : C2) / 8 * kRows;             // X1 / X2 buffer
   constexpr int kAVecs = kKChunk / 8 * kRows;                         // layer-1 A chunk
   constexpr int kAXVecs = kXVecs > kAVecs ? kXVecs : kAVecs;          // they alias
-  constexpr uint32_t kTmemCols = (C1 + C2 > C3 ? C1 + C2 : C3) <= 128 ? 128 : 256;
+  constexpr uint32_t kTmemCols = (C1 + C2 > C3 ? C1 + C2 : C3) <= 128 ? 128 : 256;   // per pipeline
   static_assert((C1 + C2 > C3 ? C1 + C2 : C3) <= 256, "TMEM budget");
 
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  uint4 *ax = reinterpret_cast<uint4 *>(smem_raw);                    // A1 chunk / X1 / X2
-  uint4 *w1s = ax + kAXVecs;                                          // [k1pad/8][C1]
+  uint4 *ax_all = reinterpret_cast<uint4 *>(smem_raw);                // 2 x (A1 chunk / X1 / X2)
+  uint4 *w1s = ax_all + G * kAXVecs;                                  // [k1pad/8][C1]
   uint4 *w2s = w1s + (P.k1pad / 8) * C1;                              // [C1/8][C2]
   uint4 *w3s = w2s + (C1 / 8) * C2;                                   // [C2/8][C3]
   float *s_b1 = reinterpret_cast<float *>(w3s + (C2 / 8) * C3);
   float *s_b2 = s_b1 + C1;
   float *s_b3 = s_b2 + C2;
-  uint64_t *s_bar = reinterpret_cast<uint64_t *>(s_b3 + C3);
-  uint32_t *s_tmem = reinterpret_cast<uint32_t *>(s_bar + 1);
+  uint64_t *s_bar = reinterpret_cast<uint64_t *>(s_b3 + C3);          // one per pipeline
+  uint32_t *s_tmem = reinterpret_cast<uint32_t *>(s_bar + 2);
 
-  const int tid = threadIdx.x;
-  const int warp = tid >> 5;
+  const int group = threadIdx.x >> 7;       // pipeline 0 / 1
+  const int tid = threadIdx.x & 127;        // row of the pipeline's tile
+  const int warp = tid >> 5;                // TMEM lane quarter (warp_id % 4 of the real warp)
+  uint4 *ax = ax_all + group * kAXVecs;
 
-  // ---- one-time setup: weights + biases -> smem, mbarrier, TMEM ----------------------
-  for (int i = tid; i < (P.k1pad / 8) * C1; i += kRows) w1s[i] = P.w1p[i];
-  for (int i = tid; i < (C1 / 8) * C2; i += kRows) w2s[i] = P.w2p[i];
-  for (int i = tid; i < (C2 / 8) * C3; i += kRows) w3s[i] = P.w3p[i];
-  for (int i = tid; i < C1; i += kRows) s_b1[i] = P.b1[i];
-  for (int i = tid; i < C2; i += kRows) s_b2[i] = P.b2[i];
-  for (int i = tid; i < C3; i += kRows) s_b3[i] = P.b3[i];
-  const uint32_t bar = smem_u32(s_bar);
-  if (tid == 0) {
-    mbar_init(bar, 1);
+  // ---- one-time setup: weights + biases -> smem, mbarriers, TMEM ----------------------
+  for (int i = threadIdx.x; i < (P.k1pad / 8) * C1; i += G * kRows) w1s[i] = P.w1p[i];
+  for (int i = threadIdx.x; i < (C1 / 8) * C2; i += G * kRows) w2s[i] = P.w2p[i];
+  for (int i = threadIdx.x; i < (C2 / 8) * C3; i += G * kRows) w3s[i] = P.w3p[i];
+  for (int i = threadIdx.x; i < C1; i += G * kRows) s_b1[i] = P.b1[i];
+  for (int i = threadIdx.x; i < C2; i += G * kRows) s_b2[i] = P.b2[i];
+  for (int i = threadIdx.x; i < C3; i += G * kRows) s_b3[i] = P.b3[i];
+  if (threadIdx.x == 0) {
+    mbar_init(smem_u32(&s_bar[0]), 1);
+    mbar_init(smem_u32(&s_bar[1]), 1);
     fence_mbar_init_cluster();
   }
-  if (warp == 0) umma::tmem_alloc(smem_u32(s_tmem), kTmemCols);
+  if (threadIdx.x < 32) umma::tmem_alloc(smem_u32(s_tmem), G * kTmemCols);
   umma::fence_proxy_async_smem();          // weights were written with st.shared
   umma::fence_before_sync();
   __syncthreads();
   umma::fence_after_sync();
-  const uint32_t tmem = *s_tmem;
+  const uint32_t tmem_base = *s_tmem;
+  const uint32_t tmem = tmem_base + group * kTmemCols;
   const uint32_t tmem_d1 = tmem, tmem_d2 = tmem + C1, tmem_d3 = tmem;
+  const uint32_t bar = smem_u32(&s_bar[group]);
 
   const uint32_t ax_addr = smem_u32(ax), w1_addr = smem_u32(w1s), w2_addr = smem_u32(w2s),
                  w3_addr = smem_u32(w3s);
-  constexpr uint32_t kIdesc1 = umma::instr_desc_bf16_f32(128, C1);
-  constexpr uint32_t kIdesc2 = umma::instr_desc_bf16_f32(128, C2);
-  constexpr uint32_t kIdesc3 = umma::instr_desc_bf16_f32(128, 128);
+  const uint32_t kIdesc1 = umma::instr_desc_16b_f32(128, C1, !P.fp16);
+  const uint32_t kIdesc2 = umma::instr_desc_16b_f32(128, C2, !P.fp16);
+  const uint32_t kIdesc3 = umma::instr_desc_16b_f32(128, 128, !P.fp16);
   uint32_t phase = 0;
 
   const int ns = P.nsample;
   const int centres_per_tile = kRows / ns;
   const int tiles_per_scene = P.npoint / centres_per_tile;
-  const float inv_unused = 0.f;
-  (void)inv_unused;
 
-  for (int tile = blockIdx.x; tile < P.num_tiles; tile += gridDim.x) {
+  for (int tile = blockIdx.x * G + group; tile < P.num_tiles; tile += gridDim.x * G) {
     const int scene = tile / tiles_per_scene;
     const int centre0 = (tile % tiles_per_scene) * centres_per_tile;
     // this thread's row: centre j, neighbour index i
@@ -161,10 +182,28 @@ sa_mlp_max_kernel(const SaParams P) {
     // ---- layer 1: gather K-chunks of A1 and accumulate D1 ------------------------------
     for (int kc0 = 0; kc0 < P.k1pad; kc0 += kKChunk) {
       const int kcn = min(kKChunk, P.k1pad - kc0);     // multiple of 16
-      for (int q = 0; q < kcn / 8; ++q) {
+      const int nq = kcn / 8;
+      // 16-byte-aligned all-feature chunks: 4 chunks (8 independent 16-byte loads) in flight
+      int q = 0;
+      if (P.feat_vec4) {
+        for (; q + 4 <= nq && kc0 + (q + 4) * 8 <= P.c; q += 4) {
+          float4 lo[4], hi[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            lo[u] = __ldg(reinterpret_cast<const float4 *>(frow + kc0 + (q + u) * 8));
+            hi[u] = __ldg(reinterpret_cast<const float4 *>(frow + kc0 + (q + u) * 8 + 4));
+          }
+#pragma unroll
+          for (int u = 0; u < 4; ++u)
+            ax[(q + u) * kRows + tid] =
+                make_uint4(pack2(lo[u].x, lo[u].y, P.fp16), pack2(lo[u].z, lo[u].w, P.fp16),
+                           pack2(hi[u].x, hi[u].y, P.fp16), pack2(hi[u].z, hi[u].w, P.fp16));
+        }
+      }
+      for (; q < nq; ++q) {
         const int k0 = kc0 + q * 8;
         float f[8];
-        if (k0 + 8 <= P.c && P.feat_vec4) {            // 8 features, 16-byte aligned rows
+        if (k0 + 8 <= P.c && P.feat_vec4) {
           const float4 a = __ldg(reinterpret_cast<const float4 *>(frow + k0));
           const float4 bq = __ldg(reinterpret_cast<const float4 *>(frow + k0 + 4));
           f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w;
@@ -179,12 +218,12 @@ sa_mlp_max_kernel(const SaParams P) {
             f[e] = v;
           }
         }
-        ax[q * kRows + tid] = make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]),
-                                         pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
+        ax[q * kRows + tid] = make_uint4(pack2(f[0], f[1], P.fp16), pack2(f[2], f[3], P.fp16),
+                                         pack2(f[4], f[5], P.fp16), pack2(f[6], f[7], P.fp16));
       }
       umma::fence_proxy_async_smem();
       umma::fence_before_sync();
-      __syncthreads();
+      group_sync(group);
       if (tid == 0) {
         umma::fence_after_sync();
         for (int ks = 0; ks < kcn / 16; ++ks) {
@@ -200,10 +239,10 @@ sa_mlp_max_kernel(const SaParams P) {
     }
 
     // ---- epilogue 1 -> X1 ; layer 2 ---------------------------------------------------
-    epilogue_rows<C1>(tmem_d1, warp, tid, s_b1, ax);
+    epilogue_rows<C1>(tmem_d1, warp, tid, s_b1, ax, P.fp16);
     umma::fence_proxy_async_smem();
     umma::fence_before_sync();
-    __syncthreads();
+    group_sync(group);
     if (tid == 0) {
       umma::fence_after_sync();
 #pragma unroll
@@ -219,10 +258,10 @@ sa_mlp_max_kernel(const SaParams P) {
     umma::fence_after_sync();
 
     // ---- epilogue 2 -> X2 ; layer 3 (transposed: channels on lanes) ---------------------
-    epilogue_rows<C2>(tmem_d2, warp, tid, s_b2, ax);
+    epilogue_rows<C2>(tmem_d2, warp, tid, s_b2, ax, P.fp16);
     umma::fence_proxy_async_smem();
     umma::fence_before_sync();
-    __syncthreads();
+    group_sync(group);
     if (tid == 0) {
       umma::fence_after_sync();
 #pragma unroll
@@ -269,18 +308,19 @@ sa_mlp_max_kernel(const SaParams P) {
       }
     }
     umma::fence_before_sync();
-    __syncthreads();       // TMEM (D3T aliases D1/D2) and the A/X buffer are free again
+    group_sync(group);     // TMEM (D3T aliases D1/D2) and the A/X buffer are free again
     umma::fence_after_sync();
   }
 
+  umma::fence_before_sync();
   __syncthreads();
-  if (warp == 0) umma::tmem_dealloc(tmem, kTmemCols);
+  if (threadIdx.x < 32) umma::tmem_dealloc(tmem_base, G * kTmemCols);
 }
 
 // w (c_out, c_in) f32 -> bf16 image [kpad/8][c_out][8]; when xyz_first, source column
 // order [xyz(3), feat(c_in-3)] becomes packed K order [feat, xyz, 0...].
-__global__ void pack_weight_kernel(int c_out, int c_in, int kpad, int xyz_first,
-                                   const float *__restrict__ w, __nv_bfloat16 *__restrict__ out) {
+__global__ void pack_weight_kernel(int c_out, int c_in, int kpad, int xyz_first, int fp16,
+                                   const float *__restrict__ w, uint16_t *__restrict__ out) {
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= c_out * kpad) return;
   const int k = t % kpad, row = t / kpad;
@@ -290,30 +330,51 @@ __global__ void pack_weight_kernel(int c_out, int c_in, int kpad, int xyz_first,
     if (xyz_first) src = (k < c_in - 3) ? k + 3 : k - (c_in - 3);
     v = w[(size_t)row * c_in + src];
   }
-  out[((size_t)(k / 8) * c_out + row) * 8 + (k % 8)] = __float2bfloat16_rn(v);
+  uint16_t bits16;
+  if (fp16) {
+    const __half h = __float2half_rn(fminf(fmaxf(v, -65504.f), 65504.f));
+    bits16 = *reinterpret_cast<const uint16_t *>(&h);
+  } else {
+    const __nv_bfloat16 h = __float2bfloat16_rn(v);
+    bits16 = *reinterpret_cast<const uint16_t *>(&h);
+  }
+  out[((size_t)(k / 8) * c_out + row) * 8 + (k % 8)] = bits16;
 }
 
 template <int C1, int C2, int C3>
-int launch_sa(const SaParams &P, cudaStream_t stream) {
+size_t sa_smem_bytes(int k1pad, int g) {
   constexpr int kXVecs = (C1 > C2 ? C1 : C2) / 8 * kRows;
   constexpr int kAVecs = kKChunk / 8 * kRows;
   constexpr int kAXVecs = kXVecs > kAVecs ? kXVecs : kAVecs;
-  const size_t smem = 16 * ((size_t)kAXVecs + (size_t)(P.k1pad / 8) * C1 + (size_t)(C1 / 8) * C2 +
-                            (size_t)(C2 / 8) * C3) + 4 * (C1 + C2 + C3) + 16;
+  return 16 * ((size_t)g * kAXVecs + (size_t)(k1pad / 8) * C1 + (size_t)(C1 / 8) * C2 +
+               (size_t)(C2 / 8) * C3) + 4 * (C1 + C2 + C3) + 32;
+}
+
+template <int C1, int C2, int C3, int G>
+int launch_sa_g(const SaParams &P, cudaStream_t stream) {
+  const size_t smem = sa_smem_bytes<C1, C2, C3>(P.k1pad, G);
   if (smem > 227 * 1024)
     return set_error(BQA_ERR_UNSUPPORTED, "sa_mlp_max: needs %zu bytes of shared memory", smem);
-  auto kern = sa_mlp_max_kernel<C1, C2, C3>;
+  auto kern = sa_mlp_max_kernel<C1, C2, C3, G>;
   BQA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  int dev = 0, sms = 148, per_sm = 1;
+  int dev = 0, sms = 148;
   BQA_CUDA(cudaGetDevice(&dev));
   BQA_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-  BQA_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kRows, smem));
-  constexpr int kTmemCols = (C1 + C2 > C3 ? C1 + C2 : C3) <= 128 ? 128 : 256;
-  per_sm = max(1, min(per_sm, 512 / kTmemCols));    // TMEM: 512 columns per SM
-  const int grid = min(P.num_tiles, sms * per_sm);
-  kern<<<grid, kRows, smem, stream>>>(P);
+  // CTAs per SM: shared memory (228 KB per SM, 1 KB reserved per CTA) and TMEM (512 columns)
+  constexpr int kTmemCols = G * ((C1 + C2 > C3 ? C1 + C2 : C3) <= 128 ? 128 : 256);
+  int per_sm = (int)((228 * 1024) / (smem + 1024));
+  per_sm = max(1, min(per_sm, 512 / kTmemCols));
+  const int grid = min((P.num_tiles + G - 1) / G, sms * per_sm);
+  kern<<<grid, G * kRows, smem, stream>>>(P);
   count_launch();
   return check_launch("sa_mlp_max_kernel");
+}
+
+// two tile pipelines per CTA when both A/X buffers fit beside the resident weights
+template <int C1, int C2, int C3>
+int launch_sa(const SaParams &P, cudaStream_t stream) {
+  if (sa_smem_bytes<C1, C2, C3>(P.k1pad, 2) <= 227 * 1024) return launch_sa_g<C1, C2, C3, 2>(P, stream);
+  return launch_sa_g<C1, C2, C3, 1>(P, stream);
 }
 
 }  // namespace
@@ -327,11 +388,11 @@ int sa_supported(int nsample, int npoint, int c, int c1, int c2, int c3) {
          (c1 == 128 && c2 == 128 && c3 == 128);
 }
 
-int pack_weight_dispatch(int c_out, int c_in, int kpad, int xyz_first, const float *w, void *packed,
-                         cudaStream_t stream) {
+int pack_weight_dispatch(int c_out, int c_in, int kpad, int xyz_first, int fp16, const float *w,
+                         void *packed, cudaStream_t stream) {
   const int total = c_out * kpad;
-  pack_weight_kernel<<<ceil_div(total, 256), 256, 0, stream>>>(c_out, c_in, kpad, xyz_first, w,
-                                                               (__nv_bfloat16 *)packed);
+  pack_weight_kernel<<<ceil_div(total, 256), 256, 0, stream>>>(c_out, c_in, kpad, xyz_first, fp16, w,
+                                                               (uint16_t *)packed);
   count_launch();
   return check_launch("pack_weight_kernel");
 }
@@ -340,7 +401,7 @@ int sa_forward_dispatch(int b, int n, int npoint, int nsample, int c, const floa
                         const float *new_xyz, const float *feat_pm, int feat_stride, const int *idx, float radius,
                         int normalize_xyz, int c1, int c2, int c3, const void *w1p, const float *b1,
                         const void *w2p, const float *b2, const void *w3p, const float *b3,
-                        float *out_cm, float *out_pm, cudaStream_t stream) {
+                        float *out_cm, float *out_pm, int fp16, cudaStream_t stream) {
   if (!sa_supported(nsample, npoint, c, c1, c2, c3))
     return set_error(BQA_ERR_UNSUPPORTED,
                      "sa_mlp_max: unsupported shape nsample=%d npoint=%d c=%d mlp=%d,%d,%d", nsample,
@@ -351,7 +412,7 @@ int sa_forward_dispatch(int b, int n, int npoint, int nsample, int c, const floa
   P.feat_stride = feat_stride;
   P.feat_vec4 = (c % 4 == 0) && (feat_stride % 4 == 0) && ((reinterpret_cast<uintptr_t>(feat_pm) & 15) == 0);
   P.xyz = xyz; P.new_xyz = new_xyz; P.feat_pm = feat_pm; P.idx = idx;
-  P.radius = radius; P.normalize_xyz = normalize_xyz;
+  P.radius = radius; P.normalize_xyz = normalize_xyz; P.fp16 = fp16;
   P.w1p = (const uint4 *)w1p; P.w2p = (const uint4 *)w2p; P.w3p = (const uint4 *)w3p;
   P.b1 = b1; P.b2 = b2; P.b3 = b3;
   P.out_cm = out_cm; P.out_pm = out_pm;

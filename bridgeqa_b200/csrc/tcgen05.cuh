@@ -24,11 +24,12 @@ __device__ __forceinline__ uint64_t smem_desc(uint32_t smem_addr, uint32_t lbo_b
          ((uint64_t)((sbo_bytes >> 4) & 0x3fffu) << 32) | (1ull << 46);
 }
 
-// 32-bit instruction descriptor for kind::f16 with BF16 A/B (both K-major) and FP32 D:
-//  [4,6) D format = 1 (f32), [7,10) A format = 1 (bf16), [10,13) B format = 1 (bf16),
+// 32-bit instruction descriptor for kind::f16 with 16-bit A/B (both K-major) and FP32 D:
+//  [4,6) D format = 1 (f32), [7,10) A format, [10,13) B format (0 = f16, 1 = bf16),
 //  bit 15 / 16 = A / B major (0 = K), [17,23) N >> 3, [24,29) M >> 4.
-__host__ __device__ constexpr uint32_t instr_desc_bf16_f32(int m, int n) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+__host__ __device__ constexpr uint32_t instr_desc_16b_f32(int m, int n, int is_bf16) {
+  return (1u << 4) | ((uint32_t)is_bf16 << 7) | ((uint32_t)is_bf16 << 10) |
+         ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
 }
 
 // ---- TMEM allocation (one full warp executes these) --------------------------------

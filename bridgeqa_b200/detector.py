@@ -21,6 +21,7 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
+from . import fused, pointnet2_utils
 from .pointnet2_modules import PointnetFPModule, PointnetSAModuleVotes
 
 
@@ -46,6 +47,7 @@ class Pointnet2Backbone(nn.Module):
                 npoint=npoint, radius=radius, nsample=nsample, mlp=spec, use_xyz=True,
                 normalize_xyz=True))
         c = 256 * width
+        self._side_streams = {}
         self.fp1 = PointnetFPModule(mlp=[c + c, c, c])
         self.fp2 = PointnetFPModule(mlp=[c + c, c, seed_feat_dim])
 
@@ -58,17 +60,53 @@ class Pointnet2Backbone(nn.Module):
             features._bqa_pm = pc[..., 3:]
         return xyz, features
 
+    def _sample_all_levels(self, xyz):
+        """Inference only.  The four FPS stages depend on coordinates alone, so levels 2-4
+        (16 small CTAs, ~0.8 ms of serial latency) run on a side stream underneath SA1's
+        ball query + MLP instead of in front of SA2/3/4.  Returns [(inds, new_xyz, event)]."""
+        main = torch.cuda.current_stream(xyz.device)
+        side = self._side_streams.get(xyz.device)
+        if side is None:
+            side = self._side_streams[xyz.device] = torch.cuda.Stream(xyz.device)
+        out = [pointnet2_utils.furthest_point_sample_with_xyz(xyz, self.sa1.npoint) + (None,)]
+        ready = torch.cuda.Event()
+        ready.record(main)
+        with torch.cuda.stream(side):
+            side.wait_event(ready)
+            cur = out[0][1]
+            for sa in (self.sa2, self.sa3, self.sa4):
+                inds, new_xyz = pointnet2_utils.furthest_point_sample_with_xyz(cur, sa.npoint)
+                done = torch.cuda.Event()
+                done.record(side)
+                for t in (inds, new_xyz):
+                    t.record_stream(main)
+                out.append((inds, new_xyz, done))
+                cur = new_xyz
+        return out
+
     def forward(self, data_dict):
         xyz, features = self._break_up_pc(data_dict["point_clouds"])
 
-        xyz, features, inds = self.sa1(xyz, features)
-        data_dict["sa1_inds"], data_dict["sa1_xyz"], data_dict["sa1_features"] = inds, xyz, features
-        xyz, features, inds = self.sa2(xyz, features)
-        data_dict["sa2_inds"], data_dict["sa2_xyz"], data_dict["sa2_features"] = inds, xyz, features
-        xyz, features, inds = self.sa3(xyz, features)
-        data_dict["sa3_xyz"], data_dict["sa3_features"] = xyz, features
-        xyz, features, inds = self.sa4(xyz, features)
-        data_dict["sa4_xyz"], data_dict["sa4_features"] = xyz, features
+        overlap = (fused.enabled() and xyz.is_cuda and not self.training
+                   and not torch.is_grad_enabled())
+        if overlap:
+            levels = self._sample_all_levels(xyz)
+            main = torch.cuda.current_stream(xyz.device)
+            outs = []
+            for sa, (inds, new_xyz, event) in zip((self.sa1, self.sa2, self.sa3, self.sa4), levels):
+                if event is not None:
+                    main.wait_event(event)
+                xyz, features, inds = sa(xyz, features, inds, new_xyz=new_xyz)
+                outs.append((xyz, features, inds))
+        else:
+            outs = []
+            for sa in (self.sa1, self.sa2, self.sa3, self.sa4):
+                xyz, features, inds = sa(xyz, features)
+                outs.append((xyz, features, inds))
+        data_dict["sa1_xyz"], data_dict["sa1_features"], data_dict["sa1_inds"] = outs[0]
+        data_dict["sa2_xyz"], data_dict["sa2_features"], data_dict["sa2_inds"] = outs[1]
+        data_dict["sa3_xyz"], data_dict["sa3_features"] = outs[2][0], outs[2][1]
+        data_dict["sa4_xyz"], data_dict["sa4_features"] = outs[3][0], outs[3][1]
 
         features = self.fp1(data_dict["sa3_xyz"], data_dict["sa4_xyz"],
                             data_dict["sa3_features"], data_dict["sa4_features"])

@@ -76,8 +76,10 @@ def ball_query(new_xyz, xyz, radius, nsample):
     nsample = int(nsample)
     idx = torch.empty((b, m, nsample), dtype=_i32, device=new_xyz.device)
     with _guard(new_xyz):
+        nbytes = N.lib().bqa_ball_query_workspace_bytes(b, n, m, nsample)
+        work = torch.empty((nbytes,), dtype=torch.uint8, device=new_xyz.device) if nbytes else None
         N.call("bqa_ball_query", b, n, m, ctypes.c_float(radius), nsample, N.ptr(new_xyz),
-               N.ptr(xyz), N.ptr(idx), N.stream_ptr(new_xyz.device))
+               N.ptr(xyz), N.ptr(idx), N.ptr(work), N.stream_ptr(new_xyz.device))
     return idx
 
 

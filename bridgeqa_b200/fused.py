@@ -15,7 +15,8 @@ from . import _native as N
 from . import ext as _ext
 from . import pytorch_utils as pt_utils
 
-_state = {"enabled": True}
+_state = {"enabled": True, "precision": "fp16"}
+_PRECISIONS = {"bf16": 0, "fp16": 1}
 _f32 = torch.float32
 
 
@@ -26,6 +27,19 @@ def set_fused(flag):
 
 def enabled():
     return _state["enabled"]
+
+
+def set_precision(name):
+    """Operand format of the fused tensor-core kernels: "fp16" (default; 11-bit mantissa like
+    TF32, the precision class of the reference's cuDNN convs; saturates at 65504) or "bf16"
+    (8-bit mantissa, fp32 range).  Accumulation is always fp32."""
+    if name not in _PRECISIONS:
+        raise ValueError("precision must be one of %s" % sorted(_PRECISIONS))
+    _state["precision"] = name
+
+
+def precision():
+    return _state["precision"]
 
 
 def _widths(mlp_module):
@@ -61,6 +75,7 @@ class PackedSA(object):
     """bf16 weight images + fp32 biases of one folded 3-layer SharedMLP, on one device."""
 
     def __init__(self, mlp_module):
+        self.precision = _PRECISIONS[_state["precision"]]
         ws = _widths(mlp_module)
         self.c_in = ws[0][0]
         self.c1, self.c2, self.c3 = ws[0][1], ws[1][1], ws[2][1]
@@ -69,9 +84,9 @@ class PackedSA(object):
             w, b = pt_utils.fold_conv_bn(blk)
             c_out, c_in = w.shape
             kpad = (c_in + 15) // 16 * 16
-            img = torch.empty(c_out * kpad, dtype=torch.bfloat16, device=w.device)
+            img = torch.empty(c_out * kpad, dtype=torch.int16, device=w.device)
             with torch.cuda.device(w.device):
-                N.call("bqa_pack_weight_bf16", c_out, c_in, kpad, 1 if li == 0 else 0, N.ptr(w),
+                N.call("bqa_pack_weight_16", c_out, c_in, kpad, 1 if li == 0 else 0, self.precision, N.ptr(w),
                        N.ptr(img), N.stream_ptr(w.device))
             self.packed.append(img)
             self.bias.append(b)
@@ -81,7 +96,8 @@ class PackedSA(object):
 def weights_signature(module):
     """Changes whenever a parameter / BN buffer of `module` is replaced, moved or written in
     place (load_state_dict, optimizer step, .to()), so folded weights are never stale."""
-    return tuple((t.data_ptr(), t._version) for t in list(module.parameters()) + list(module.buffers()))
+    return (_state["precision"],) + tuple(
+        (t.data_ptr(), t._version) for t in list(module.parameters()) + list(module.buffers()))
 
 
 def fold_sa_mlp(mlp_module):
@@ -125,7 +141,7 @@ def sa_forward(xyz, new_xyz, features, radius, nsample, normalize_xyz, packed):
                packed.c1, packed.c2, packed.c3,
                N.ptr(packed.packed[0]), N.ptr(packed.bias[0]), N.ptr(packed.packed[1]),
                N.ptr(packed.bias[1]), N.ptr(packed.packed[2]), N.ptr(packed.bias[2]),
-               N.ptr(out_cm), N.ptr(out_pm), N.stream_ptr(xyz.device))
+               N.ptr(out_cm), N.ptr(out_pm), packed.precision, N.stream_ptr(xyz.device))
     out_cm._bqa_pm = out_pm
     return out_cm
 

@@ -143,13 +143,15 @@ class PointnetSAModuleVotes(nn.Module):
         self._fused_cache = None       # folded weights are stale once BN stats can move
         return super().train(mode)
 
-    def forward(self, xyz, features=None, inds=None):
+    def forward(self, xyz, features=None, inds=None, new_xyz=None):
+        """`new_xyz` (optional, beyond the reference signature): the centres xyz[inds] when the
+        caller already has them (e.g. from the FPS kernel's epilogue), skipping the gather."""
         if inds is not None:
             assert inds.shape[1] == self.npoint
-        if self.npoint is not None:
-            inds, new_xyz = _centres(xyz, self.npoint, inds)
-        else:
+        if self.npoint is None:
             new_xyz = None
+        elif inds is None or new_xyz is None:
+            inds, new_xyz = _centres(xyz, self.npoint, inds)
 
         if self._can_fuse(xyz, features):
             sig = fused.weights_signature(self.mlp_module)

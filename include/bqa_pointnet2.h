@@ -67,9 +67,14 @@ BQA_API int bqa_gather_points_grad(int b, int c, int n, int m, const float *grad
  * replaces: ball_query(new_xyz (B,M,3), xyz (B,N,3), radius, nsample) -> (B,M,nsample)
  *           src/ball_query.cpp:8-32, kernel src/ball_query_gpu.cu:9-54.
  * First `nsample` indices k (ascending) with d2 < radius*radius, first hit back-fills
- * the row, empty ball -> zeros.  */
+ * the row, empty ball -> zeros.
+ * workspace: optional device scratch of bqa_ball_query_workspace_bytes(b,n,m,nsample) bytes
+ * (0 for small scenes).  With it, large scenes are scanned in index-ordered segments by
+ * several CTAs per query block (~2.5x faster at 40k points); with NULL a single CTA per
+ * query block scans the whole scene.  The result is identical either way.  */
+BQA_API long long bqa_ball_query_workspace_bytes(int b, int n, int m, int nsample);
 BQA_API int bqa_ball_query(int b, int n, int m, float radius, int nsample, const float *new_xyz,
-                   const float *xyz, int *idx, void *stream);
+                   const float *xyz, int *idx, void *workspace, void *stream);
 
 /* ---- grouping -----------------------------------------------------------------
  * replaces: group_points / group_points_grad, src/group_points.cpp:12-62,
@@ -99,9 +104,12 @@ BQA_API int bqa_three_interpolate_grad(int b, int c, int n, int m, const float *
  * subtract centre, divide by radius, group features, concat) -> SharedMLP of three
  * [1x1 conv -> BN -> ReLU] blocks (pytorch_utils.py:11-36) -> max_pool2d over nsample
  * (pointnet2_modules.py:259-262), without materialising the grouped tensor or any
- * activation in HBM.  bf16 operands, fp32 accumulation on tcgen05 tensor cores.
+ * activation in HBM.  16-bit operands, fp32 accumulation on tcgen05 tensor cores
+ * (kind::f16).  `precision`: 0 = bf16 operands (8-bit mantissa, fp32 range); 1 = fp16
+ * operands (11-bit mantissa -- the same as TF32, which is what the reference's cuDNN convs
+ * use by default -- values saturate at +-65504).  Same speed either way.
  *
- * bqa_pack_weight_bf16: w (c_out, c_in) f32 row-major (BN already folded) -> the bf16
+ * bqa_pack_weight_16: w (c_out, c_in) f32 row-major (BN already folded) -> the 16-bit
  *   shared-memory image the kernel loads, [k_pad/8][c_out][8], k_pad a multiple of 16,
  *   zero padded.  xyz_first=1: source columns are [xyz(3), feat(c_in-3)] (torch.cat order
  *   at pointnet2_utils.py:357) and are re-ordered to [feat, xyz] to match the kernel's
@@ -112,12 +120,12 @@ BQA_API int bqa_three_interpolate_grad(int b, int c, int n, int m, const float *
  *   POINT-MAJOR f32 (NULL iff c == 0) whose consecutive points are feat_stride floats apart
  *   (feat_stride >= c; scenes are n*feat_stride apart -- lets SA1 read the features straight
  *   out of the (b,n,3+c) input cloud); idx (b,npoint,nsample) i32 from bqa_ball_query;
- *   w{1,2,3}p packed with k_pad = roundup16(c+3), c1, c2; b{1,2,3} f32 biases.
+ *   w{1,2,3}p packed (same `precision`) with k_pad = roundup16(c+3), c1, c2; b{1,2,3} f32.
  *   grouped xyz is (xyz[idx] - new_xyz) and, when normalize_xyz, divided by `radius`.
  *   out_cm (b,c3,npoint) f32 = the reference's new_features; out_pm (b,npoint,c3) f32
  *   optional point-major copy for the next layer (NULL to skip). */
-BQA_API int bqa_pack_weight_bf16(int c_out, int c_in, int k_pad, int xyz_first, const float *w,
-                                 void *packed, void *stream);
+BQA_API int bqa_pack_weight_16(int c_out, int c_in, int k_pad, int xyz_first, int precision,
+                               const float *w, void *packed, void *stream);
 BQA_API int bqa_sa_mlp_max_supported(int nsample, int npoint, int c, int c1, int c2, int c3);
 BQA_API int bqa_sa_mlp_max_forward(int b, int n, int npoint, int nsample, int c, const float *xyz,
                                    const float *new_xyz, const float *feat_pm, int feat_stride,
@@ -125,7 +133,7 @@ BQA_API int bqa_sa_mlp_max_forward(int b, int n, int npoint, int nsample, int c,
                                    float radius, int normalize_xyz, int c1, int c2, int c3,
                                    const void *w1p, const float *b1, const void *w2p,
                                    const float *b2, const void *w3p, const float *b3,
-                                   float *out_cm, float *out_pm, void *stream);
+                                   float *out_cm, float *out_pm, int precision, void *stream);
 
 /* ---- layout helper -------------------------------------------------------------
  * (b,c,n) channel-major -> (b,n,c) point-major, the layout the fused SA kernel gathers

@@ -34,6 +34,8 @@ def test_library_builds_loads_and_exports_header_symbols():
     assert lib.bqa_last_error() == b""
     assert lib.bqa_fps_scratch_bytes(16, 40000) == 0      # register-resident
     assert lib.bqa_fps_scratch_bytes(2, 200000) == 2 * 200000 * 4
+    assert lib.bqa_ball_query_workspace_bytes(16, 512, 256, 16) == 0        # small scene: one segment
+    assert lib.bqa_ball_query_workspace_bytes(16, 40000, 2048, 64) > 16 * 2048 * 64 * 4
 
 
 def test_sass_is_sm100a_and_uses_cluster_and_bulk_copy():
@@ -56,7 +58,7 @@ def test_sass_is_sm100a_and_uses_cluster_and_bulk_copy():
 def test_invalid_arguments_return_status_and_message_without_a_gpu():
     from bridgeqa_b200 import _native
     lib = _native.lib()
-    rc = lib.bqa_ball_query(-1, 1, 1, ctypes.c_float(0.1), 1, None, None, None, None)
+    rc = lib.bqa_ball_query(-1, 1, 1, ctypes.c_float(0.1), 1, None, None, None, None, None)
     assert rc == 1 and b"must be >= 0" in lib.bqa_last_error()
     rc = lib.bqa_furthest_point_sampling(1, 10, 4, None, None, None, None, None)
     assert rc == 1 and b"NULL" in lib.bqa_last_error()
