@@ -222,6 +222,11 @@ def main():
     if args.impl == "reference":
         return run_reference_arm(args)
 
+    # stdout carries exactly ONE JSON line: libraries that print there (NCCL's version banner)
+    # are sent to stderr until the line is ready
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+
     import torch
     import torch.distributed as dist
     import bridgeqa_b200
@@ -381,7 +386,10 @@ def main():
             r = cpu_reference_run(steps=1, warmup=0, sample_scenes=4)
             line["cpu_baseline"] = {"value": r["value"], "unit": UNIT, "cores": r["cores"],
                                     "kind": "port", "sample": r["sample"]}
-        print(json.dumps(line))
+        sys.stdout.flush()
+        os.dup2(real_stdout, 1)
+        print(json.dumps(line), flush=True)
+        os.dup2(2, 1)
     if world > 1:
         dist.destroy_process_group()
     return 0
