@@ -1,0 +1,53 @@
+"""The unmodified reference Python layer imports and constructs on top of the compat shims
+(CPU only: construction, API surface and checkpoint keys; the ops themselves need a GPU).
+Skipped where /root/reference is not mounted (the GPU box)."""
+import os
+import subprocess
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF = "/root/reference"
+
+SCRIPT = r'''
+import os, sys
+sys.path.insert(0, %(root)r)
+from bridgeqa_b200 import compat
+compat.install(level=%(level)r)
+os.chdir(%(ref)r)                      # backbone_module.py:8 appends os.getcwd()/lib
+sys.path.insert(0, %(ref)r)
+if %(level)r == "ext":
+    sys.path.insert(0, os.path.join(%(ref)r, "lib", "pointnet2"))
+from models.backbone_module import Pointnet2Backbone
+from models.voting_module import VotingModule
+import torch
+net = Pointnet2Backbone(input_feature_dim=7)
+from bridgeqa_b200 import detector
+mine = detector.Pointnet2Backbone(input_feature_dim=7)
+assert sorted(net.state_dict()) == sorted(mine.state_dict())
+assert all(net.state_dict()[k].shape == mine.state_dict()[k].shape for k in mine.state_dict())
+mine.load_state_dict(net.state_dict(), strict=True)
+import pointnet2._ext as e
+assert e.furthest_point_sampling.__module__ == "bridgeqa_b200.ext"
+mod = sys.modules[type(net.sa1).__module__]
+print("OK", type(net.sa1).__module__, getattr(mod, "__file__", ""))
+try:
+    net({"point_clouds": torch.randn(1, 3000, 10)})
+except RuntimeError as ex:
+    assert "CUDA" in str(ex), ex       # no CPU fallback: the op refuses CPU tensors
+    print("REFUSED_CPU")
+'''
+
+
+@pytest.mark.skipif(not os.path.isdir(REF), reason="reference tree not mounted")
+@pytest.mark.parametrize("level", ["ext", "modules"])
+def test_reference_models_import_on_top_of_shims(level):
+    r = subprocess.run([sys.executable, "-c", SCRIPT % {"root": ROOT, "ref": REF, "level": level}],
+                       stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout
+    assert "OK" in r.stdout and "REFUSED_CPU" in r.stdout, r.stdout
+    if level == "ext":
+        assert "/root/reference/lib/pointnet2/pointnet2_modules.py" in r.stdout, r.stdout
+    else:
+        assert "bridgeqa_b200" in r.stdout, r.stdout
