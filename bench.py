@@ -199,8 +199,9 @@ def algorithmic_work(name, dims):
         flops = 2 * b * npt * ns * ((c + 3) * c1 + c1 * c2 + c2 * c3)
         byts = b * (4 * npt * ns + 4 * npt * ns * (c + 3) + 4 * c3 * npt)
         return {"bytes": byts, "flops": flops, "bound": "tensor"}
-    if name == "bqa_fp_forward":
-        b, n, m, ck, cs, c1, c2 = dims[:7]
+    if name == "bqa_fp_mlp_forward":
+        b, n, m, ck, cs = dims[:5]
+        c1, c2 = dims[7:9]               # dims[5:7] = row strides
         flops = 2 * b * n * ((ck + cs) * c1 + c1 * c2)
         byts = 4 * b * (ck * m + cs * n + c2 * n + 3 * n + 3 * m)
         return {"bytes": byts, "flops": flops, "bound": "tensor"}

@@ -67,6 +67,13 @@ int sa_forward_dispatch(int b, int n, int npoint, int nsample, int c, const floa
                         const void *w2p, const float *b2, const void *w3p, const float *b3,
                         float *out_cm, float *out_pm, int fp16, cudaStream_t stream);
 
+int fp_supported(int n, int m, int c_known, int c_skip, int c1, int c2);
+int fp_forward_dispatch(int b, int n, int m, int c_known, int c_skip, const float *unknown,
+                        const float *known, const float *known_feat, int known_stride,
+                        const float *skip_feat, int skip_stride, int c1, int c2, const void *w,
+                        const float *b1, const float *b2, float *out_cm, float *out_pm, int fp16,
+                        cudaStream_t stream);
+
 }  // namespace bqa
 
 using namespace bqa;
@@ -206,6 +213,25 @@ int bqa_sa_mlp_max_forward(int b, int n, int npoint, int nsample, int c, const f
   return sa_forward_dispatch(b, n, npoint, nsample, c, xyz, new_xyz, feat_pm, feat_stride, idx, radius,
                              normalize_xyz, c1, c2, c3, w1p, b1, w2p, b2, w3p, b3, out_cm, out_pm,
                              precision, (cudaStream_t)stream);
+}
+
+int bqa_fp_mlp_supported(int n, int m, int c_known, int c_skip, int c1, int c2) {
+  return fp_supported(n, m, c_known, c_skip, c1, c2);
+}
+
+int bqa_fp_mlp_forward(int b, int n, int m, int c_known, int c_skip, const float *unknown,
+                       const float *known, const float *known_feat, int known_stride,
+                       const float *skip_feat, int skip_stride, int c1, int c2, const void *w,
+                       const float *b1, const float *b2, float *out_cm, float *out_pm, int precision,
+                       void *stream) {
+  NONNEG(b); NONNEG(n); NONNEG(m);
+  if ((long long)b * n == 0) return BQA_OK;
+  BQA_REQUIRE(precision == 0 || precision == 1, "%s: precision must be 0 (bf16) or 1 (fp16)", __func__);
+  PTR(unknown); PTR(known); PTR(known_feat); PTR(skip_feat); PTR(w); PTR(b1); PTR(b2); PTR(out_cm);
+  BQA_REQUIRE(known_stride >= c_known && skip_stride >= c_skip, "%s: row strides too small", __func__);
+  return fp_forward_dispatch(b, n, m, c_known, c_skip, unknown, known, known_feat, known_stride,
+                             skip_feat, skip_stride, c1, c2, w, b1, b2, out_cm, out_pm, precision,
+                             (cudaStream_t)stream);
 }
 
 }  // extern "C"

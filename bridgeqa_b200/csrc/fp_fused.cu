@@ -1,0 +1,318 @@
+// fp_fused.cu -- fused feature-propagation layer for inference on sm_100a:
+//   three_nn -> inverse-distance weights -> three_interpolate -> concat with the skip
+//   features -> 2 x [1x1 conv + folded BN + ReLU] on tcgen05 tensor cores.
+//
+// Replaces, for eval-mode forward, PointnetFPModule.forward
+// (/root/reference/lib/pointnet2/pointnet2_modules.py:376-421): three_nn_kernel,
+// sqrt / reciprocal / sum / div elementwise kernels, three_interpolate_kernel, torch.cat,
+// and 2 x [cuDNN conv, BN, ReLU] -- the interpolated (B, C2, n) tensor, the concatenated
+// (B, C1+C2, n) tensor and the hidden activation never touch HBM.
+//
+// One CTA of 128 threads owns a tile of 128 unknown points (thread = point = TMEM lane):
+//   * three_nn over the scene's known set staged in shared memory (same strict-`<` cascade in
+//     ascending index as the stand-alone op, so the neighbours are bit-identical);
+//   * layer 1, K = C_known + C_skip = 512 in 8 chunks of 64: the thread builds its row of the
+//     A operand (interpolated channels fma(p3,w3,fma(p1,w1,p2*w2)), then its own skip
+//     channels) as 16-bit K-major vectors while the bulk-copy engine streams the matching
+//     32 KB slice of W1 into the other stage (cp.async.bulk -> mbarrier) and the tensor core
+//     works on the previous chunk (tcgen05.commit -> mbarrier per stage);
+//   * epilogue 1 keeps relu(D1 + b1) in shared memory as the A operand of layer 2, whose
+//     4 weight slices flow through the same two stages;
+//   * epilogue 2 writes relu(D2 + b2) both channel-major (the reference layout) and
+//     point-major (for the next fused layer), each coalesced.
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+
+#include "common.cuh"
+#include "tcgen05.cuh"
+
+namespace bqa {
+namespace {
+
+constexpr int kRows = 128;
+constexpr int kChunk = 64;         // K per weight slice
+constexpr int kWidth = 256;        // C1 == C2 == 256 (both FP layers of the backbone)
+constexpr int kKnownTile = 512;    // known points staged per pass of three_nn
+
+__device__ __forceinline__ uint32_t pack16(float lo, float hi, int fp16) {
+  if (fp16) {
+    lo = fminf(fmaxf(lo, -65504.f), 65504.f);
+    hi = fminf(fmaxf(hi, -65504.f), 65504.f);
+    __half2 v = __floats2half2_rn(lo, hi);
+    return *reinterpret_cast<uint32_t *>(&v);
+  }
+  __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t *>(&v);
+}
+
+__device__ __forceinline__ void bulk_load(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+      ::"r"(dst), "l"(src), "r"(bytes), "r"(bar)
+      : "memory");
+}
+
+struct FpParams {
+  int b, n, m, c_known, c_skip;
+  int known_stride, skip_stride;          // floats between consecutive points
+  const float *unknown, *known;           // (b,n,3), (b,m,3)
+  const float *known_feat, *skip_feat;    // point-major
+  const uint4 *w;                         // W1 image [(ck+cs)/8][256] then W2 image [256/8][256], 16-byte vectors
+  const float *b1, *b2;
+  float *out_cm, *out_pm;
+  int fp16;
+  int num_tiles, tiles_per_scene;
+};
+
+__global__ void __launch_bounds__(kRows)
+fp_mlp_kernel(const FpParams P) {
+  constexpr int kAVecs = kChunk / 8 * kRows;          // 1024 x 16 B = 16 KB per stage
+  constexpr int kWVecs = kChunk / 8 * kWidth;         // 2048 x 16 B = 32 KB per stage
+  constexpr int kXVecs = kWidth / 8 * kRows;          // 4096 x 16 B = 64 KB
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  uint4 *a_st = reinterpret_cast<uint4 *>(smem_raw);                  // [2][kAVecs]
+  uint4 *w_st = a_st + 2 * kAVecs;                                    // [2][kWVecs]
+  uint4 *x1 = w_st + 2 * kWVecs;                                      // [kXVecs]
+  float *s_known = reinterpret_cast<float *>(x1 + kXVecs);            // [kKnownTile * 3]
+  float *s_b1 = s_known + kKnownTile * 3;
+  float *s_b2 = s_b1 + kWidth;
+  uint64_t *s_bar = reinterpret_cast<uint64_t *>(s_b2 + kWidth);      // wfull[2], mdone[2]
+  uint32_t *s_tmem = reinterpret_cast<uint32_t *>(s_bar + 4);
+
+  const int tid = threadIdx.x;
+  const int warp = tid >> 5;
+  for (int i = tid; i < kWidth; i += kRows) { s_b1[i] = P.b1[i]; s_b2[i] = P.b2[i]; }
+  const uint32_t wfull0 = smem_u32(&s_bar[0]), mdone0 = smem_u32(&s_bar[2]);
+  if (tid == 0) {
+    for (int i = 0; i < 4; ++i) mbar_init(smem_u32(&s_bar[i]), 1);
+    fence_mbar_init_cluster();
+  }
+  if (warp == 0) umma::tmem_alloc(smem_u32(s_tmem), 512);
+  umma::fence_before_sync();
+  __syncthreads();
+  umma::fence_after_sync();
+  const uint32_t tmem = *s_tmem;
+  const uint32_t tmem_d1 = tmem, tmem_d2 = tmem + kWidth;
+  const uint32_t a_addr = smem_u32(a_st), w_addr = smem_u32(w_st), x_addr = smem_u32(x1);
+  const uint32_t idesc = umma::instr_desc_16b_f32(128, kWidth, !P.fp16);
+
+  const int nk1 = (P.c_known + P.c_skip) / kChunk;   // weight slices of layer 1
+  const int nk2 = kWidth / kChunk;                   // of layer 2
+  const int nchunks = nk1 + nk2;
+  uint32_t gchunk = 0;                               // running slice counter (stage / parity)
+
+  for (int tile = blockIdx.x; tile < P.num_tiles; tile += gridDim.x) {
+    const int scene = tile / P.tiles_per_scene;
+    const int row0 = (tile % P.tiles_per_scene) * kRows;
+    const bool live = row0 + tid < P.n;
+    const int j = live ? row0 + tid : P.n - 1;       // clamp: dead rows compute, never store
+
+    // first weight slice can fly while three_nn runs (both stages are idle between tiles)
+    if (tid == 0) {
+      const uint32_t s = gchunk & 1;
+      mbar_arrive_expect_tx(wfull0 + 8 * s, kWVecs * 16);
+      bulk_load(w_addr + s * kWVecs * 16, P.w, kWVecs * 16, wfull0 + 8 * s);
+    }
+
+    // ---- three_nn (interpolate_gpu.cu:9-58 semantics) + weights (pointnet2_modules.py:399-402)
+    float ux, uy, uz;
+    {
+      const float *u = P.unknown + ((size_t)scene * P.n + j) * 3;
+      ux = u[0]; uy = u[1]; uz = u[2];
+    }
+    float best1 = INFINITY, best2 = INFINITY, best3 = INFINITY;
+    int i1 = 0, i2 = 0, i3 = 0;
+    const float *known = P.known + (size_t)scene * P.m * 3;
+    for (int base = 0; base < P.m; base += kKnownTile) {
+      const int tn = min(kKnownTile, P.m - base);
+      __syncthreads();
+      for (int t = tid; t < tn * 3; t += kRows) s_known[t] = known[(size_t)base * 3 + t];
+      __syncthreads();
+#pragma unroll 4
+      for (int t = 0; t < tn; ++t) {
+        const float d = sqdist3(ux, uy, uz, s_known[t * 3], s_known[t * 3 + 1], s_known[t * 3 + 2]);
+        const int k = base + t;
+        if (d < best1) {
+          best3 = best2; i3 = i2; best2 = best1; i2 = i1; best1 = d; i1 = k;
+        } else if (d < best2) {
+          best3 = best2; i3 = i2; best2 = d; i2 = k;
+        } else if (d < best3) {
+          best3 = d; i3 = k;
+        }
+      }
+    }
+    float w1, w2, w3;
+    {
+      const float r1 = __fdiv_rn(1.0f, __fadd_rn(__fsqrt_rn(best1), 1e-8f));
+      const float r2 = __fdiv_rn(1.0f, __fadd_rn(__fsqrt_rn(best2), 1e-8f));
+      const float r3 = __fdiv_rn(1.0f, __fadd_rn(__fsqrt_rn(best3), 1e-8f));
+      const float norm = __fadd_rn(__fadd_rn(r1, r2), r3);
+      w1 = __fdiv_rn(r1, norm); w2 = __fdiv_rn(r2, norm); w3 = __fdiv_rn(r3, norm);
+    }
+    const float *f1 = P.known_feat + ((size_t)scene * P.m + i1) * P.known_stride;
+    const float *f2 = P.known_feat + ((size_t)scene * P.m + i2) * P.known_stride;
+    const float *f3 = P.known_feat + ((size_t)scene * P.m + i3) * P.known_stride;
+    const float *fs = P.skip_feat + ((size_t)scene * P.n + j) * P.skip_stride;
+
+    for (int c = 0; c < nchunks; ++c) {
+      const uint32_t g = gchunk + c, s = g & 1;
+      // stage s^1 is free once the MMAs of slice g-1 are done: prefetch the next weights
+      if (c + 1 < nchunks) {
+        if (c >= 1) mbar_wait(mdone0 + 8 * (s ^ 1), ((g - 1) >> 1) & 1);
+        if (tid == 0) {
+          mbar_arrive_expect_tx(wfull0 + 8 * (s ^ 1), kWVecs * 16);
+          bulk_load(w_addr + (s ^ 1) * kWVecs * 16, P.w + (size_t)(c + 1) * kWVecs, kWVecs * 16,
+                    wfull0 + 8 * (s ^ 1));
+        }
+      }
+      if (c < nk1) {
+        // ---- this thread's row of the layer-1 A operand, channels [c*64, c*64+64) ----------
+        uint4 *dst = a_st + s * kAVecs;
+        const int k0 = c * kChunk;
+        if (k0 < P.c_known) {
+#pragma unroll 2
+          for (int q = 0; q < kChunk / 8; ++q) {
+            float v[8];
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+              const float4 p1 = __ldg(reinterpret_cast<const float4 *>(f1 + k0 + q * 8 + h * 4));
+              const float4 p2 = __ldg(reinterpret_cast<const float4 *>(f2 + k0 + q * 8 + h * 4));
+              const float4 p3 = __ldg(reinterpret_cast<const float4 *>(f3 + k0 + q * 8 + h * 4));
+              v[h * 4 + 0] = __fmaf_rn(p3.x, w3, __fmaf_rn(p1.x, w1, __fmul_rn(p2.x, w2)));
+              v[h * 4 + 1] = __fmaf_rn(p3.y, w3, __fmaf_rn(p1.y, w1, __fmul_rn(p2.y, w2)));
+              v[h * 4 + 2] = __fmaf_rn(p3.z, w3, __fmaf_rn(p1.z, w1, __fmul_rn(p2.z, w2)));
+              v[h * 4 + 3] = __fmaf_rn(p3.w, w3, __fmaf_rn(p1.w, w1, __fmul_rn(p2.w, w2)));
+            }
+            dst[q * kRows + tid] = make_uint4(pack16(v[0], v[1], P.fp16), pack16(v[2], v[3], P.fp16),
+                                              pack16(v[4], v[5], P.fp16), pack16(v[6], v[7], P.fp16));
+          }
+        } else {
+          const float *src = fs + (k0 - P.c_known);
+#pragma unroll 4
+          for (int q = 0; q < kChunk / 8; ++q) {
+            const float4 a = __ldg(reinterpret_cast<const float4 *>(src + q * 8));
+            const float4 bq = __ldg(reinterpret_cast<const float4 *>(src + q * 8 + 4));
+            dst[q * kRows + tid] = make_uint4(pack16(a.x, a.y, P.fp16), pack16(a.z, a.w, P.fp16),
+                                              pack16(bq.x, bq.y, P.fp16), pack16(bq.z, bq.w, P.fp16));
+          }
+        }
+      }
+      umma::fence_proxy_async_smem();
+      umma::fence_before_sync();
+      __syncthreads();
+      if (tid == 0) {
+        mbar_wait(wfull0 + 8 * s, (g >> 1) & 1);
+        umma::fence_after_sync();
+        const bool layer1 = c < nk1;
+        const uint32_t abase = layer1 ? a_addr + s * kAVecs * 16
+                                      : x_addr + (uint32_t)(c - nk1) * (kChunk / 8) * kRows * 16;
+#pragma unroll
+        for (int ks = 0; ks < kChunk / 16; ++ks) {
+          const uint64_t ad = umma::smem_desc(abase + (uint32_t)(2 * ks) * kRows * 16, kRows * 16, 128);
+          const uint64_t bd = umma::smem_desc(w_addr + s * kWVecs * 16 + (uint32_t)(2 * ks) * kWidth * 16,
+                                              kWidth * 16, 128);
+          const uint32_t acc = layer1 ? ((c | ks) != 0) : (((c - nk1) | ks) != 0);
+          umma::mma_bf16_ss(layer1 ? tmem_d1 : tmem_d2, ad, bd, idesc, acc);
+        }
+        umma::commit(mdone0 + 8 * s);
+      }
+      if (c == nk1 - 1) {
+        // ---- epilogue 1: X1 = relu(D1 + b1) as the 16-bit A operand of layer 2 ------------
+        mbar_wait(mdone0 + 8 * s, (g >> 1) & 1);
+        umma::fence_after_sync();
+#pragma unroll 2
+        for (int c0 = 0; c0 < kWidth; c0 += 32) {
+          uint32_t v[32];
+          umma::ld_32x32b_x32(tmem_d1 + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0, v);
+          umma::wait_ld();
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            uint32_t p[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const int col = c0 + q * 8 + e * 2;
+              const float lo = fmaxf(__uint_as_float(v[q * 8 + e * 2]) + s_b1[col], 0.f);
+              const float hi = fmaxf(__uint_as_float(v[q * 8 + e * 2 + 1]) + s_b1[col + 1], 0.f);
+              p[e] = pack16(lo, hi, P.fp16);
+            }
+            x1[(c0 / 8 + q) * kRows + tid] = make_uint4(p[0], p[1], p[2], p[3]);
+          }
+        }
+      }
+    }
+    gchunk += nchunks;
+
+    // ---- epilogue 2: out = relu(D2 + b2), channel-major and point-major -------------------
+    {
+      const uint32_t g = gchunk - 1, s = g & 1;
+      mbar_wait(mdone0 + 8 * s, (g >> 1) & 1);
+      umma::fence_after_sync();
+      float *opm = P.out_pm ? P.out_pm + ((size_t)scene * P.n + j) * kWidth : nullptr;
+      float *ocm = P.out_cm + (size_t)scene * kWidth * P.n + j;
+#pragma unroll 2
+      for (int c0 = 0; c0 < kWidth; c0 += 32) {
+        uint32_t v[32];
+        umma::ld_32x32b_x32(tmem_d2 + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0, v);
+        umma::wait_ld();
+        float o[32];
+#pragma unroll
+        for (int e = 0; e < 32; ++e) o[e] = fmaxf(__uint_as_float(v[e]) + s_b2[c0 + e], 0.f);
+        if (live) {
+#pragma unroll
+          for (int e = 0; e < 32; ++e) ocm[(size_t)(c0 + e) * P.n] = o[e];     // lanes = consecutive points
+          if (opm) {
+#pragma unroll
+            for (int e = 0; e < 32; e += 4)
+              *reinterpret_cast<float4 *>(opm + c0 + e) = make_float4(o[e], o[e + 1], o[e + 2], o[e + 3]);
+          }
+        }
+      }
+    }
+    umma::fence_before_sync();
+    __syncthreads();       // TMEM, X1 and both stages are free for the next tile
+    umma::fence_after_sync();
+  }
+  __syncthreads();
+  if (warp == 0) umma::tmem_dealloc(tmem, 512);
+}
+
+}  // namespace
+
+int fp_supported(int n, int m, int c_known, int c_skip, int c1, int c2) {
+  if (c1 != kWidth || c2 != kWidth) return 0;
+  if (c_known <= 0 || c_skip <= 0 || c_known % kChunk || c_skip % kChunk) return 0;
+  if (n <= 0 || m <= 0) return 0;
+  return 1;
+}
+
+int fp_forward_dispatch(int b, int n, int m, int c_known, int c_skip, const float *unknown,
+                        const float *known, const float *known_feat, int known_stride,
+                        const float *skip_feat, int skip_stride, int c1, int c2, const void *w,
+                        const float *b1, const float *b2, float *out_cm, float *out_pm, int fp16,
+                        cudaStream_t stream) {
+  if (!fp_supported(n, m, c_known, c_skip, c1, c2))
+    return set_error(BQA_ERR_UNSUPPORTED, "fp_mlp: unsupported shape c_known=%d c_skip=%d mlp=%d,%d",
+                     c_known, c_skip, c1, c2);
+  if ((known_stride % 4) || (skip_stride % 4) || (reinterpret_cast<uintptr_t>(known_feat) & 15) ||
+      (reinterpret_cast<uintptr_t>(skip_feat) & 15) || (reinterpret_cast<uintptr_t>(out_pm) & 15))
+    return set_error(BQA_ERR_INVALID_ARG, "fp_mlp: point-major features must be 16-byte aligned rows");
+  FpParams P;
+  P.b = b; P.n = n; P.m = m; P.c_known = c_known; P.c_skip = c_skip;
+  P.known_stride = known_stride; P.skip_stride = skip_stride;
+  P.unknown = unknown; P.known = known; P.known_feat = known_feat; P.skip_feat = skip_feat;
+  P.w = (const uint4 *)w; P.b1 = b1; P.b2 = b2; P.out_cm = out_cm; P.out_pm = out_pm; P.fp16 = fp16;
+  P.tiles_per_scene = ceil_div(n, kRows);
+  P.num_tiles = b * P.tiles_per_scene;
+  const size_t smem = 16 * (2 * (size_t)(kChunk / 8 * kRows) + 2 * (size_t)(kChunk / 8 * kWidth) +
+                            (size_t)(kWidth / 8 * kRows)) + 4 * (kKnownTile * 3 + 2 * kWidth) + 32 + 16;
+  BQA_CUDA(cudaFuncSetAttribute(fp_mlp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int dev = 0, sms = 148;
+  BQA_CUDA(cudaGetDevice(&dev));
+  BQA_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  const int grid = min(P.num_tiles, sms);
+  fp_mlp_kernel<<<grid, kRows, smem, stream>>>(P);
+  count_launch();
+  return check_launch("fp_mlp_kernel");
+}
+
+}  // namespace bqa

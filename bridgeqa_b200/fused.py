@@ -67,8 +67,26 @@ def sa_supported(mlp_module, nsample, npoint, c_feat):
                                                 ws[0][1], ws[1][1], ws[2][1]))
 
 
-def fp_supported(mlp_module, c_known, c_skip):
-    return False
+def _fp_widths(mlp_module):
+    blocks = list(mlp_module)
+    if len(blocks) != 2:
+        return None
+    ws = []
+    for blk in blocks:
+        conv = getattr(blk, "conv", None)
+        if conv is None or not isinstance(conv, torch.nn.Conv2d) or conv.kernel_size != (1, 1):
+            return None
+        if not isinstance(getattr(blk, "activation", None), torch.nn.ReLU):
+            return None
+        ws.append((conv.in_channels, conv.out_channels))
+    return ws if ws[0][1] == ws[1][0] else None
+
+
+def fp_supported(mlp_module, n, m, c_known, c_skip):
+    ws = _fp_widths(mlp_module)
+    if ws is None or ws[0][0] != c_known + c_skip:
+        return False
+    return bool(N.lib().bqa_fp_mlp_supported(int(n), int(m), int(c_known), int(c_skip), ws[0][1], ws[1][1]))
 
 
 class PackedSA(object):
@@ -104,8 +122,30 @@ def fold_sa_mlp(mlp_module):
     return PackedSA(mlp_module)
 
 
+class PackedFP(object):
+    """Layer-1 and layer-2 weight images back to back (the kernel streams them as 32 KB
+    slices) + fp32 biases of one folded 2-layer SharedMLP."""
+
+    def __init__(self, mlp_module):
+        self.precision = _PRECISIONS[_state["precision"]]
+        ws = _fp_widths(mlp_module)
+        self.c1, self.c2 = ws[0][1], ws[1][1]
+        folded = [pt_utils.fold_conv_bn(blk) for blk in mlp_module]
+        sizes = [w.shape[0] * w.shape[1] for w, _ in folded]
+        dev = folded[0][0].device
+        self.image = torch.empty(sum(sizes), dtype=torch.int16, device=dev)
+        off = 0
+        with torch.cuda.device(dev):
+            for (w, _), sz in zip(folded, sizes):
+                c_out, c_in = w.shape
+                N.call("bqa_pack_weight_16", c_out, c_in, c_in, 0, self.precision, N.ptr(w),
+                       ctypes.c_void_p(self.image.data_ptr() + 2 * off), N.stream_ptr(dev))
+                off += sz
+        self.bias = [b for _, b in folded]
+
+
 def fold_fp_mlp(mlp_module):
-    return [pt_utils.fold_conv_bn(block) for block in mlp_module]
+    return PackedFP(mlp_module)
 
 
 def point_major(features):
@@ -146,5 +186,20 @@ def sa_forward(xyz, new_xyz, features, radius, nsample, normalize_xyz, packed):
     return out_cm
 
 
-def fp_forward(unknown, known, unknow_feats, known_feats, folded):
-    raise RuntimeError("fused FP kernel not built")
+def fp_forward(unknown, known, unknow_feats, known_feats, packed):
+    """-> new_features (B, C2, n) fp32, with a point-major twin attached as ._bqa_pm."""
+    N.check_tensor(unknown, "unknown", _f32)
+    N.check_tensor(known, "known", _f32)
+    b, n, _ = unknown.shape
+    m = known.size(1)
+    kpm = point_major(known_feats)
+    spm = point_major(unknow_feats)
+    out_cm = torch.empty((b, packed.c2, n), dtype=_f32, device=unknown.device)
+    out_pm = torch.empty((b, n, packed.c2), dtype=_f32, device=unknown.device)
+    with torch.cuda.device(unknown.device):
+        N.call("bqa_fp_mlp_forward", b, n, m, kpm.size(2), spm.size(2), N.ptr(unknown), N.ptr(known),
+               N.ptr(kpm), kpm.stride(1), N.ptr(spm), spm.stride(1), packed.c1, packed.c2,
+               N.ptr(packed.image), N.ptr(packed.bias[0]), N.ptr(packed.bias[1]), N.ptr(out_cm),
+               N.ptr(out_pm), packed.precision, N.stream_ptr(unknown.device))
+    out_cm._bqa_pm = out_pm
+    return out_cm

@@ -223,10 +223,12 @@ class PointnetFPModule(nn.Module):
     def forward(self, unknown, known, unknow_feats, known_feats):
         if (known is not None and unknow_feats is not None and fused.enabled()
                 and not self.training and not torch.is_grad_enabled() and unknown.is_cuda
-                and fused.fp_supported(self.mlp, known_feats.size(1), unknow_feats.size(1))):
-            if self._fused_cache is None:
-                self._fused_cache = fused.fold_fp_mlp(self.mlp)
-            return fused.fp_forward(unknown, known, unknow_feats, known_feats, self._fused_cache)
+                and fused.fp_supported(self.mlp, unknown.size(1), known.size(1),
+                                       known_feats.size(1), unknow_feats.size(1))):
+            sig = fused.weights_signature(self.mlp)
+            if self._fused_cache is None or self._fused_cache[0] != sig:
+                self._fused_cache = (sig, fused.fold_fp_mlp(self.mlp))
+            return fused.fp_forward(unknown, known, unknow_feats, known_feats, self._fused_cache[1])
 
         if known is not None:
             dist, idx = pointnet2_utils.three_nn(unknown, known)

@@ -135,6 +135,24 @@ BQA_API int bqa_sa_mlp_max_forward(int b, int n, int npoint, int nsample, int c,
                                    const float *b2, const void *w3p, const float *b3,
                                    float *out_cm, float *out_pm, int precision, void *stream);
 
+/* ---- fused feature-propagation layer (inference) -----------------------------------
+ * replaces PointnetFPModule.forward (pointnet2_modules.py:376-421): three_nn ->
+ * 1/(dist+1e-8) weights normalised over the 3 neighbours -> three_interpolate -> cat with
+ * the skip features -> two [1x1 conv -> BN -> ReLU] blocks, in one kernel.
+ * unknown (b,n,3), known (b,m,3) f32; known_feat (b,m,c_known) and skip_feat (b,n,c_skip)
+ * POINT-MAJOR f32 with the given row strides (floats, multiples of 4, 16-byte aligned);
+ * layer-1 input channel order is [interpolated(c_known), skip(c_skip)] like torch.cat at
+ * pointnet2_modules.py:413.  w: layer-1 image (k_pad = c_known+c_skip) immediately followed
+ * by the layer-2 image (k_pad = c1), both from bqa_pack_weight_16(xyz_first=0) with the same
+ * `precision`; b1, b2 f32.  out_cm (b,c2,n) f32; out_pm (b,n,c2) f32 optional.
+ * bqa_fp_mlp_supported: c1 == c2 == 256 and c_known, c_skip multiples of 64. */
+BQA_API int bqa_fp_mlp_supported(int n, int m, int c_known, int c_skip, int c1, int c2);
+BQA_API int bqa_fp_mlp_forward(int b, int n, int m, int c_known, int c_skip, const float *unknown,
+                               const float *known, const float *known_feat, int known_stride,
+                               const float *skip_feat, int skip_stride, int c1, int c2,
+                               const void *w, const float *b1, const float *b2, float *out_cm,
+                               float *out_pm, int precision, void *stream);
+
 /* ---- layout helper -------------------------------------------------------------
  * (b,c,n) channel-major -> (b,n,c) point-major, the layout the fused SA kernel gathers
  * from (one contiguous row per neighbour).  Replaces nothing in the reference; it is

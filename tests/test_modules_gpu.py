@@ -223,3 +223,38 @@ def test_fused_cache_follows_weight_updates():
             bridgeqa_b200.set_fused(True)
     assert not torch.allclose(a, b)
     assert relerr(b.cpu().numpy(), c.cpu().numpy()) < 1e-2
+
+
+FUSED_FP_CASES = [
+    # (B, n, m, c_known, c_skip)
+    (2, 512, 256, 256, 256),
+    (2, 1024, 512, 256, 256),
+    (1, 300, 700, 128, 64),       # ragged tile, known set larger than one smem pass, other widths
+    (2, 129, 2, 64, 64),          # fewer than 3 known points: infinite distances -> zero weights
+]
+
+
+@pytest.mark.parametrize("precision,tol", [("fp16", 1e-3), ("bf16", 1e-2)])
+@pytest.mark.parametrize("B,n,m,ck,cs", FUSED_FP_CASES)
+def test_fused_fp_kernel_matches_unfused_fp32(B, n, m, ck, cs, precision, tol, _restore_fused):
+    """Fused FP (three_nn + interpolate + concat + 2-layer MLP on tcgen05) vs the un-fused fp32
+    path of the same module.  Neighbour indices are bit-identical by construction (same cascade);
+    features within 1e-3 (fp16 operands) / 1e-2 (bf16) of the tensor's max."""
+    bridgeqa_b200.set_precision(precision)
+    fp = synthetic.fill_state_dict(pm.PointnetFPModule(mlp=[ck + cs, 256, 256]), seed=21).cuda().eval()
+    xyz = synthetic.make_batch(B, n + m, 0, first_scene=85)[..., :3].contiguous().cuda()
+    unknown, known = xyz[:, :n].contiguous(), xyz[:, n:].contiguous()
+    uf = torch.randn(B, cs, n, device="cuda")
+    kf = torch.randn(B, ck, m, device="cuda")
+    with torch.no_grad():
+        bridgeqa_b200.set_fused(False)
+        ref = fp(unknown, known, uf, kf)
+        bridgeqa_b200.set_fused(True)
+        from bridgeqa_b200 import _native
+        before = _native.launch_count()
+        got = fp(unknown, known, uf, kf)
+        assert _native.launch_count() - before <= 5      # transposes (no twins here) + packs + 1 fused kernel
+    assert got.shape == ref.shape == (B, 256, n)
+    err = relerr(got.cpu().numpy(), ref.cpu().numpy())
+    assert err < tol, err
+    assert torch.equal(got._bqa_pm, got.transpose(1, 2).contiguous())
