@@ -22,6 +22,9 @@
 //   the winner minimises (bitrev(k mod bs), k) where bs = opt_n_threads(n) is the block
 //   size the reference would have used -- that is what its pairwise tree with
 //   "ties keep the lower slot" (sampling_gpu.cu:59-65,115-168) computes.
+#include <cstdio>
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace bqa {
@@ -94,7 +97,10 @@ namespace {
 //      barrier); every warp folds the cs candidates that landed in its own shared memory.
 // Variants that were measured and lost: packed fp32x2 math for step 1 (FFMA2 issues at half
 // rate: 43 vs 22 cycles per point), one warp folding all 512 thread candidates from shared
-// memory (574 cycles), handing results over through shared memory instead of redux/shfl.
+// memory (574 cycles), handing results over through shared memory instead of redux/shfl, and
+// two scenes interleaved per 8-CTA cluster with a 17th communication warp (bit-exact, 28 %
+// fewer SM-cycles per scene, but 2024 cycles per pair-iteration vs 1517 for one scene on a
+// 6-CTA cluster, so the batch of 16 finishes later: 2.06 ms vs 1.58 ms).
 template <int P, int T>
 __global__ void __launch_bounds__(T, 1)
 fps_cluster_kernel(int n, int m, int cs, uint32_t cs_magic, int bits,
@@ -382,10 +388,12 @@ int max_clusters(int cs) {
 // modelled time  waves * (fixed + per-point work / cs)  where waves = ceil(b / clusters that
 // are co-resident on this GPU) -- measured on B200: 8-CTA clusters co-reside 15 at a time,
 // 6-CTA 22, 4-CTA 33, so 16 scenes of 40k points run best on 6-CTA clusters.
-static void fps_plan(int b, int n, int *cs_out, int *per_thread_out) {
+struct FpsPlan { int cs; int per_thread; };
+
+static FpsPlan fps_plan(int b, int n) {
   static int cached_clusters[17] = {0};
   static const int kSizes[] = {1, 2, 4, 6, 8, 16};
-  int best_cs = 0;
+  FpsPlan best = {0, kMaxP + 1};
   double best_t = 0;
   for (int cs : kSizes) {
     const int per_thread = ceil_div(n, cs * kT);
@@ -402,13 +410,12 @@ static void fps_plan(int b, int n, int *cs_out, int *per_thread_out) {
       ncl = cached_clusters[cs];
       if (ncl <= 0) continue;
     }
-    const int waves = ceil_div(b, ncl);
-    // cycles per iteration: ~800 fixed (+350 for the cluster hop) + ~0.06 per point per CTA
-    const double t = waves * ((cs == 1 ? 600.0 : 1000.0) + 0.06 * (double)n / cs);
-    if (!best_cs || t < best_t) { best_cs = cs; best_t = t; }
+    // cycles per iteration (measured): ~1000 of argmax chain (~600 without the cluster hop)
+    // + ~36 per point held by a thread
+    const double t = ceil_div(b, ncl) * ((cs == 1 ? 600.0 : 1000.0) + 36.0 * per_thread);
+    if (!best.cs || t < best_t) { best = {cs, per_thread}; best_t = t; }
   }
-  *cs_out = best_cs;
-  *per_thread_out = best_cs ? ceil_div(n, best_cs * kT) : kMaxP + 1;
+  return best;
 }
 
 long long fps_scratch_bytes(int b, int n) {
@@ -423,8 +430,15 @@ int fps_dispatch(int b, int n, int m, const float *xyz, int *idxs, float *new_xy
   while ((1 << bits) < bs) ++bits;
   if ((long long)n >= (1ll << 22) * bs) return set_error(BQA_ERR_UNSUPPORTED, "fps: n=%d too large", n);
 
-  int cs, per_thread;
-  fps_plan(b, n, &cs, &per_thread);
+  FpsPlan plan = fps_plan(b, n);
+  static const char *dbg = getenv("BQA_FPS_DEBUG");
+  if (dbg) {
+    // developer override of the cluster size (e.g. BQA_FPS_DEBUG=8) and a one-line plan report
+    const int ocs = atoi(dbg);
+    if (ocs > 0 && ocs <= 16 && ceil_div(n, ocs * kT) <= kMaxP) plan = {ocs, ceil_div(n, ocs * kT)};
+    fprintf(stderr, "[bqa fps] b=%d n=%d m=%d -> cs=%d per_thread=%d\n", b, n, m, plan.cs, plan.per_thread);
+  }
+  const int cs = plan.cs, per_thread = plan.per_thread;
   if (per_thread > kMaxP) {
     if (!scratch)
       return set_error(BQA_ERR_INVALID_ARG,
