@@ -208,6 +208,57 @@ def algorithmic_work(name, dims):
     return {"bytes": 0, "bound": "hbm"}
 
 
+def run_train_mode(args, torch, dist, device, world, rank, real_stdout):
+    """configs[3]: fwd + bwd + gradient all-reduce of the detector (C = 132), train-mode BN."""
+    from bridgeqa_b200 import _native, detector, synthetic, training
+    feats = 132
+    net = synthetic.fill_state_dict(detector.VoteNetDetector(feats), seed=0).to(device)
+    loss_fn = training.ProjectionLoss().to(device)
+    bsz = args.train_batch
+    pc = synthetic.make_batch(bsz, NUM_POINTS, feats, first_scene=rank * bsz).to(device)
+    torch.backends.cudnn.allow_tf32 = True          # torch's (and the reference's) default
+    torch.backends.cuda.matmul.allow_tf32 = True
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        training.train_step(net, loss_fn, pc)
+    barrier()
+    l0 = _native.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        loss = training.train_step(net, loss_fn, pc)
+    e1.record()
+    barrier()
+    t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=device)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t[0])
+    if rank == 0:
+        nparam = sum(p.numel() for p in net.parameters())
+        line = {"metric": "scenes/sec DET train step (fwd+bwd+grad all-reduce), 40k pts, C=132",
+                "value": bsz * world * args.steps / (ms / 1e3), "unit": UNIT, "n_gpus": world,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "tf32",
+                "data": "synthetic",
+                "config": {"workload": "VoteNetDetector fwd+bwd, train-mode BN, %d scenes/GPU, un-fused "
+                                       "differentiable operators + torch MLPs, one flat NCCL all-reduce of %d "
+                                       "fp32 gradients" % (bsz, nparam)},
+                "gpu_launches": _native.launch_count() - l0, "loss": float(loss)}
+        sys.stdout.flush()
+        os.dup2(real_stdout, 1)
+        print(json.dumps(line), flush=True)
+        os.dup2(2, 1)
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -217,6 +268,9 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--unfused", action="store_true", help="force the un-fused operator path")
     ap.add_argument("--tf32", action="store_true", help="allow TF32 in torch convs of the un-fused path")
+    ap.add_argument("--mode", default="forward", choices=["forward", "train"],
+                    help="forward = BASELINE headline (configs[1]); train = DET train step, configs[3]")
+    ap.add_argument("--train-batch", type=int, default=16, help="scenes per GPU in --mode train")
     ap.add_argument("--precision", default="fp16", choices=["fp16", "bf16"],
                     help="operand format of the fused tensor-core kernels (fp32 accumulate)")
     args = ap.parse_args()
@@ -250,6 +304,8 @@ def main():
     torch.backends.cuda.matmul.allow_tf32 = bool(args.tf32)
 
     _native.lib()   # fail loudly here if the CUDA library is missing
+    if args.mode == "train":
+        return run_train_mode(args, torch, dist, device, world, rank, real_stdout)
     net = synthetic.fill_state_dict(detector.Pointnet2Backbone(input_feature_dim=FEATURES), seed=0)
     net = net.to(device).eval()
 
