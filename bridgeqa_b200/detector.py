@@ -56,8 +56,11 @@ class Pointnet2Backbone(nn.Module):
         xyz = pc[..., :3].contiguous()
         features = pc[..., 3:].transpose(1, 2).contiguous() if pc.size(-1) > 3 else None
         if features is not None:
-            # the input cloud already is the point-major layout the fused SA kernel gathers from
-            features._bqa_pm = pc[..., 3:]
+            # the input cloud already is the point-major layout the fused SA kernel gathers from;
+            # when the channel count allows 16-byte loads (C % 4 == 0, e.g. the 132-d multiview
+            # config) one packed copy makes the rows aligned (the view starts 12 bytes in)
+            c = pc.size(-1) - 3
+            features._bqa_pm = pc[..., 3:].contiguous() if (c % 4 == 0 and c >= 16) else pc[..., 3:]
         return xyz, features
 
     def _sample_all_levels(self, xyz):
