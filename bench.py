@@ -454,10 +454,22 @@ def main():
         kernels.sort(key=lambda r: -r["share"])
         top = kernels[0] if kernels else None
         roofline = None
+        traffic = None
+        try:   # dram__bytes_read + dram__bytes_write per launch from the committed ncu --set full capture
+            prof = json.load(open(os.path.join(ROOT, "profiles", "r1_kernels_ncu.json")))
+            if top and top["kernel"] == "bqa_furthest_point_sampling" and top["dims"][:3] == [BATCH, NUM_POINTS, 2048]:
+                hit = [k for k in prof if k["kernel"].startswith("fps_cluster_kernel<14")]
+                if hit:
+                    traffic = hit[0]["dram_read_bytes"] + hit[0]["dram_write_bytes"]
+        except Exception:
+            traffic = None
         if top:
             roofline = {"kernel": "%s%s" % (top["kernel"], top["dims"]), "bound": top["bound"],
                         "achieved": top["achieved"], "peak": top["peak"], "unit": top["unit"],
-                        "frac": top["frac"], "traffic": None, "peak_source": peaks["source"],
+                        "frac": top["frac"], "traffic": traffic,
+                        "traffic_source": "profiles/r1_kernels_ncu.json (ncu --set full, per launch)" if traffic else None,
+                        "algorithmic_bytes": algorithmic_work(top["kernel"], top["dims"])["bytes"],
+                        "peak_source": peaks["source"],
                         "share_of_step": top["share"], "ms": top["ms"]}
             if "us_per_iter" in top:
                 roofline["us_per_iter"] = top["us_per_iter"]
