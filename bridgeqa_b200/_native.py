@@ -26,10 +26,12 @@ _SIGNATURES = {
     "bqa_launch_count": ([], _LL),
     "bqa_fps_scratch_bytes": ([_I, _I], _LL),
     "bqa_furthest_point_sampling": ([_I, _I, _I, _P, _P, _P, _P, _P], _I),
+    "bqa_furthest_point_sampling_slice": ([_I, _I, _I, _I, _I, _P, _P, _P, _P, _I, _P], _I),
     "bqa_gather_points": ([_I, _I, _I, _I, _P, _P, _P, _P], _I),
     "bqa_gather_points_grad": ([_I, _I, _I, _I, _P, _P, _P, _P], _I),
     "bqa_ball_query_workspace_bytes": ([_I, _I, _I, _I], _LL),
     "bqa_ball_query": ([_I, _I, _I, _F, _I, _P, _P, _P, _P, _P], _I),
+    "bqa_ball_query_slice": ([_I, _I, _I, _I, _I, _F, _I, _P, _P, _P, _P, _P], _I),
     "bqa_group_points": ([_I, _I, _I, _I, _I, _P, _P, _P, _P], _I),
     "bqa_group_points_grad": ([_I, _I, _I, _I, _I, _P, _P, _P, _P], _I),
     "bqa_three_nn": ([_I, _I, _I, _P, _P, _P, _P, _P], _I),
@@ -40,6 +42,8 @@ _SIGNATURES = {
     "bqa_fp_mlp_forward": ([_I, _I, _I, _I, _I, _P, _P, _P, _I, _P, _I, _I, _I, _P, _P, _P, _P, _P, _I, _P], _I),
     "bqa_pack_weight_16": ([_I, _I, _I, _I, _I, _P, _P, _P], _I),
     "bqa_sa_mlp_max_supported": ([_I, _I, _I, _I, _I, _I], _I),
+    "bqa_sa_mlp_max_forward_slice": ([_I, _I, _I, _I, _I, _I, _I, _P, _P, _P, _I, _P, _F, _I, _I, _I, _I,
+                                      _P, _P, _P, _P, _P, _P, _P, _P, _I, _P], _I),
     "bqa_sa_mlp_max_forward": ([_I, _I, _I, _I, _I, _P, _P, _P, _I, _P, _F, _I, _I, _I, _I,
                                 _P, _P, _P, _P, _P, _P, _P, _P, _I, _P], _I),
 }

@@ -40,11 +40,12 @@ int ref_opt_n_threads(int work_size) {
 }
 
 // dispatchers implemented in the kernel translation units
-int fps_dispatch(int b, int n, int m, const float *xyz, int *idxs, float *new_xyz, float *scratch,
-                 cudaStream_t stream);
+int fps_dispatch(int b, int n, int m, int j_begin, int j_end, const float *xyz, int *idxs,
+                 float *new_xyz, float *scratch, bool exclusive, cudaStream_t stream);
 long long fps_scratch_bytes(int b, int n);
 int ball_query_dispatch(int b, int n, int m, float radius, int nsample, const float *new_xyz,
-                        const float *xyz, int *idx, void *workspace, cudaStream_t stream);
+                        const float *xyz, int *idx, void *workspace, cudaStream_t stream,
+                        int q_stride, int q_offset);
 long long ball_query_workspace_bytes(int b, int n, int m, int nsample);
 int gather_rows_dispatch(int b, int c, int n, long long e_total, const float *points, const int *idx,
                          float *out, cudaStream_t stream);
@@ -65,7 +66,8 @@ int sa_forward_dispatch(int b, int n, int npoint, int nsample, int c, const floa
                         const float *new_xyz, const float *feat_pm, int feat_stride, const int *idx, float radius,
                         int normalize_xyz, int c1, int c2, int c3, const void *w1p, const float *b1,
                         const void *w2p, const float *b2, const void *w3p, const float *b3,
-                        float *out_cm, float *out_pm, int fp16, cudaStream_t stream);
+                        float *out_cm, float *out_pm, int fp16, cudaStream_t stream, int npoint_total,
+                        int j_offset);
 
 int fp_supported(int n, int m, int c_known, int c_skip, int c1, int c2);
 int fp_forward_dispatch(int b, int n, int m, int c_known, int c_skip, const float *unknown,
@@ -95,7 +97,19 @@ int bqa_furthest_point_sampling(int b, int n, int m, const float *xyz, int *idxs
   if (b == 0 || m == 0) return BQA_OK;
   BQA_REQUIRE(n > 0, "%s: n must be > 0 when m > 0", __func__);
   PTR(xyz); PTR(idxs);
-  return fps_dispatch(b, n, m, xyz, idxs, new_xyz, scratch, (cudaStream_t)stream);
+  return fps_dispatch(b, n, m, 1, m, xyz, idxs, new_xyz, scratch, false, (cudaStream_t)stream);
+}
+
+int bqa_furthest_point_sampling_slice(int b, int n, int m, int j_begin, int j_end, const float *xyz,
+                                      int *idxs, float *new_xyz, float *state, int exclusive,
+                                      void *stream) {
+  NONNEG(b); NONNEG(n); NONNEG(m);
+  BQA_REQUIRE(j_begin >= 1 && j_begin <= j_end && j_end <= m, "%s: need 1 <= j_begin <= j_end <= m", __func__);
+  if (b == 0 || m == 0) return BQA_OK;
+  BQA_REQUIRE(n > 0, "%s: n must be > 0 when m > 0", __func__);
+  PTR(xyz); PTR(idxs);
+  return fps_dispatch(b, n, m, j_begin, j_end, xyz, idxs, new_xyz, state, exclusive != 0,
+                      (cudaStream_t)stream);
 }
 
 int bqa_gather_points(int b, int c, int n, int m, const float *points, const int *idx, float *out,
@@ -127,7 +141,20 @@ int bqa_ball_query(int b, int n, int m, float radius, int nsample, const float *
   PTR(new_xyz); PTR(idx);
   if (n > 0) PTR(xyz);
   return ball_query_dispatch(b, n, m, radius, nsample, new_xyz, xyz, idx, workspace,
-                             (cudaStream_t)stream);
+                             (cudaStream_t)stream, m, 0);
+}
+
+int bqa_ball_query_slice(int b, int n, int m_total, int j_begin, int j_count, float radius, int nsample,
+                         const float *new_xyz, const float *xyz, int *idx, void *workspace,
+                         void *stream) {
+  NONNEG(b); NONNEG(n); NONNEG(m_total); NONNEG(nsample);
+  BQA_REQUIRE(j_begin >= 0 && j_count >= 0 && j_begin + j_count <= m_total,
+              "%s: slice [%d, %d) outside [0, %d)", __func__, j_begin, j_begin + j_count, m_total);
+  if ((long long)b * j_count * nsample == 0) return BQA_OK;
+  PTR(new_xyz); PTR(idx);
+  if (n > 0) PTR(xyz);
+  return ball_query_dispatch(b, n, j_count, radius, nsample, new_xyz, xyz, idx, workspace,
+                             (cudaStream_t)stream, m_total, j_begin);
 }
 
 int bqa_group_points(int b, int c, int n, int npoints, int nsample, const float *points,
@@ -212,7 +239,27 @@ int bqa_sa_mlp_max_forward(int b, int n, int npoint, int nsample, int c, const f
   BQA_REQUIRE(!normalize_xyz || radius > 0.f, "%s: radius must be > 0", __func__);
   return sa_forward_dispatch(b, n, npoint, nsample, c, xyz, new_xyz, feat_pm, feat_stride, idx, radius,
                              normalize_xyz, c1, c2, c3, w1p, b1, w2p, b2, w3p, b3, out_cm, out_pm,
-                             precision, (cudaStream_t)stream);
+                             precision, (cudaStream_t)stream, npoint, 0);
+}
+
+int bqa_sa_mlp_max_forward_slice(int b, int n, int npoint_total, int j_begin, int j_count, int nsample,
+                                 int c, const float *xyz, const float *new_xyz, const float *feat_pm,
+                                 int feat_stride, const int *idx, float radius, int normalize_xyz,
+                                 int c1, int c2, int c3, const void *w1p, const float *b1,
+                                 const void *w2p, const float *b2, const void *w3p, const float *b3,
+                                 float *out_cm, float *out_pm, int precision, void *stream) {
+  NONNEG(b); NONNEG(n); NONNEG(npoint_total); NONNEG(nsample); NONNEG(c);
+  BQA_REQUIRE(j_begin >= 0 && j_count >= 0 && j_begin + j_count <= npoint_total,
+              "%s: slice [%d, %d) outside [0, %d)", __func__, j_begin, j_begin + j_count, npoint_total);
+  if ((long long)b * j_count == 0) return BQA_OK;
+  BQA_REQUIRE(precision == 0 || precision == 1, "%s: precision must be 0 (bf16) or 1 (fp16)", __func__);
+  PTR(xyz); PTR(new_xyz); PTR(idx); PTR(w1p); PTR(b1); PTR(w2p); PTR(b2); PTR(w3p); PTR(b3); PTR(out_cm);
+  BQA_REQUIRE((c == 0) == (feat_pm == nullptr), "%s: feat_pm must be NULL iff c == 0", __func__);
+  BQA_REQUIRE(c == 0 || feat_stride >= c, "%s: feat_stride=%d < c=%d", __func__, feat_stride, c);
+  BQA_REQUIRE(!normalize_xyz || radius > 0.f, "%s: radius must be > 0", __func__);
+  return sa_forward_dispatch(b, n, j_count, nsample, c, xyz, new_xyz, feat_pm, feat_stride, idx, radius,
+                             normalize_xyz, c1, c2, c3, w1p, b1, w2p, b2, w3p, b3, out_cm, out_pm,
+                             precision, (cudaStream_t)stream, npoint_total, j_begin);
 }
 
 int bqa_fp_mlp_supported(int n, int m, int c_known, int c_skip, int c1, int c2) {

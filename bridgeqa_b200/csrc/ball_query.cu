@@ -58,7 +58,8 @@ constexpr int kSortMax = 4096;     // centres per scene the shared-memory sort h
 
 // one CTA per scene: perm = argsort(new_xyz[:, 0]) (ties by index), bitonic in shared memory
 __global__ void __launch_bounds__(1024)
-sort_queries_kernel(int m, const float *__restrict__ new_xyz_all, int *__restrict__ perm_all) {
+sort_queries_kernel(int m, int q_stride, int q_offset, const float *__restrict__ new_xyz_all,
+                    int *__restrict__ perm_all) {
   __shared__ unsigned long long keys[kSortMax];
   const int scene = blockIdx.x;
   int npow = 1;
@@ -66,7 +67,7 @@ sort_queries_kernel(int m, const float *__restrict__ new_xyz_all, int *__restric
   for (int i = threadIdx.x; i < npow; i += blockDim.x) {
     unsigned long long k = ~0ull;
     if (i < m) {
-      const uint32_t u = __float_as_uint(new_xyz_all[((size_t)scene * m + i) * 3]);
+      const uint32_t u = __float_as_uint(new_xyz_all[((size_t)scene * q_stride + q_offset + i) * 3]);
       const uint32_t ord = (u & 0x80000000u) ? ~u : (u | 0x80000000u);     // float order -> uint order
       k = ((unsigned long long)ord << 32) | (uint32_t)i;
     }
@@ -89,7 +90,8 @@ sort_queries_kernel(int m, const float *__restrict__ new_xyz_all, int *__restric
 }
 
 __global__ void __launch_bounds__(kQueries)
-ball_query_kernel(int n, int m, float radius2, float rfilt, int nsample, int nseg, int seg_len,
+ball_query_kernel(int n, int m, int q_stride, int q_offset, float radius2, float rfilt, int nsample,
+                  int nseg, int seg_len,
                   const float *__restrict__ new_xyz_all, const float *__restrict__ xyz_all,
                   int *__restrict__ idx_all, BqWorkspace ws) {
   __shared__ __align__(128) float tile[kStages][kTile * 3];
@@ -107,13 +109,17 @@ ball_query_kernel(int n, int m, float radius2, float rfilt, int nsample, int nse
   const int k_end = min(n, k_begin + seg_len);
 
   float qx = 0.f, qy = 0.f, qz = 0.f;
+  // the m queries of a scene are centres [q_offset, q_offset + m) of its q_stride centres (a
+  // slice of the sampling); the workspace is indexed by the local query number
+  const size_t qglob = (size_t)scene * q_stride + q_offset;
   if (live) {
-    const float *q = new_xyz_all + ((size_t)scene * m + j) * 3;
+    const float *q = new_xyz_all + (qglob + j) * 3;
     qx = q[0]; qy = q[1]; qz = q[2];
   }
   // where this thread appends its hits: the final row (one segment) or its segment's list
   const size_t qlin = (size_t)scene * m + (live ? j : 0);
-  int *row = nseg == 1 ? idx_all + qlin * nsample : ws.hits + (qlin * nseg + seg) * nsample;
+  int *row = nseg == 1 ? idx_all + (qglob + (live ? j : 0)) * nsample
+                       : ws.hits + (qlin * nseg + seg) * nsample;
 
   // The bulk copy needs 16-byte aligned source and size.  `head` points (0..3) are read
   // with plain loads so the bulk part starts aligned; the tail (< 4 points) likewise.
@@ -232,7 +238,7 @@ ball_query_kernel(int n, int m, float radius2, float rfilt, int nsample, int nse
       }
       remaining -= c;
     }
-    idx_all[((size_t)scene * m + jq) * nsample + slot] = found ? value : first_hit;
+    idx_all[(qglob + jq) * nsample + slot] = found ? value : first_hit;
   }
 }
 
@@ -261,7 +267,8 @@ long long ball_query_workspace_bytes(int b, int n, int m, int nsample) {
 }
 
 int ball_query_dispatch(int b, int n, int m, float radius, int nsample, const float *new_xyz,
-                        const float *xyz, int *idx, void *workspace, cudaStream_t stream) {
+                        const float *xyz, int *idx, void *workspace, cudaStream_t stream,
+                        int q_stride, int q_offset) {
   const float radius2 = radius * radius;  // ball_query_gpu.cu:21, fp32 product
   const int nseg = workspace ? plan_segments(b, n, m) : 1;
   BqWorkspace ws = {nullptr, nullptr, nullptr, nullptr};
@@ -270,7 +277,7 @@ int ball_query_dispatch(int b, int n, int m, float radius, int nsample, const fl
   if (workspace && want_sort(n, m)) {
     ws.perm = reinterpret_cast<int *>(wsp);
     wsp += perm_bytes(b, m);
-    sort_queries_kernel<<<b, 1024, 0, stream>>>(m, new_xyz, ws.perm);
+    sort_queries_kernel<<<b, 1024, 0, stream>>>(m, q_stride, q_offset, new_xyz, ws.perm);
     count_launch();
     if (int rc = check_launch("sort_queries_kernel")) return rc;
   }
@@ -286,8 +293,8 @@ int ball_query_dispatch(int b, int n, int m, float radius, int nsample, const fl
   }
   if (b > 65535) return set_error(BQA_ERR_UNSUPPORTED, "ball_query: batch too large");
   dim3 grid((unsigned)ceil_div(m, kQueries), (unsigned)nseg, (unsigned)b);
-  ball_query_kernel<<<grid, kQueries, 0, stream>>>(n, m, radius2, rfilt, nsample, nseg, seg_len, new_xyz,
-                                                   xyz, idx, ws);
+  ball_query_kernel<<<grid, kQueries, 0, stream>>>(n, m, q_stride, q_offset, radius2, rfilt, nsample, nseg,
+                                                   seg_len, new_xyz, xyz, idx, ws);
   count_launch();
   return check_launch("ball_query_kernel");
 }

@@ -103,9 +103,13 @@ namespace {
 // 6-CTA cluster, so the batch of 16 finishes later: 2.06 ms vs 1.58 ms).
 template <int P, int T>
 __global__ void __launch_bounds__(T, 1)
-fps_cluster_kernel(int n, int m, int cs, uint32_t cs_magic, int bits,
+fps_cluster_kernel(int n, int m, int j_begin, int j_end, int cs, uint32_t cs_magic, int bits,
                    const float *__restrict__ xyz_all, int *__restrict__ idx_all,
-                   float *__restrict__ new_xyz_all FPS_TRACE_ARG) {
+                   float *__restrict__ new_xyz_all, float *__restrict__ state_all FPS_TRACE_ARG) {
+  // Samples j_begin .. j_end-1 are produced by this launch (1 <= j_begin <= j_end <= m).  A
+  // launch that does not start at 1 resumes from the running min-distances a previous launch
+  // left in state_all (b,n), one that does not end at m leaves them there: the sampling can be
+  // issued in slices so that consumers of the first centres run under the later slices.
   static_assert(T == 512, "slot <-> index arithmetic below assumes 512 threads (= max bs)");
   constexpr int NW = T / 32;
   constexpr int kLogT = 9;
@@ -143,6 +147,7 @@ fps_cluster_kernel(int n, int m, int cs, uint32_t cs_magic, int bits,
       z = xyz[(size_t)k * 3 + 2];
       const float mag = __fmaf_rn(z, z, __fmaf_rn(x, x, __fmul_rn(y, y)));
       if (!((double)mag <= 1e-3)) t = 1e10f;  // sampling_gpu.cu:100-101, sampling.cpp:74-76
+      if (j_begin > 1) t = state_all[(size_t)scene * n + k];   // resume (-inf marks skipped points)
     }
     px[p] = x; py[p] = y; pz[p] = z; td[p] = t;
     sx[p * T + tid] = x;
@@ -165,14 +170,15 @@ fps_cluster_kernel(int n, int m, int cs, uint32_t cs_magic, int bits,
     __syncthreads();
   }
 
-  float x1 = xyz[0], y1 = xyz[1], z1 = xyz[2];
-  if (rank == 0 && tid == 0 && m > 0) {
+  const int last = j_begin > 1 ? idxs[j_begin - 1] : 0;       // written by the previous slice
+  float x1 = xyz[(size_t)last * 3], y1 = xyz[(size_t)last * 3 + 1], z1 = xyz[(size_t)last * 3 + 2];
+  if (rank == 0 && tid == 0 && m > 0 && j_begin == 1) {
     idxs[0] = 0;  // sampling_gpu.cu:85-86
     if (new_xyz) { new_xyz[0] = x1; new_xyz[1] = y1; new_xyz[2] = z1; }
   }
 
   FPS_TRACE_BEGIN
-  for (int j = 1; j < m; ++j) {
+  for (int j = j_begin; j < j_end; ++j) {
     const int buf = j & 1;
     // ---- 1. update the P running min-distances, keep the thread's max --------------------
     float best = -1.f;
@@ -203,7 +209,7 @@ fps_cluster_kernel(int n, int m, int cs, uint32_t cs_magic, int bits,
       x1 = sx[old]; y1 = sy[old]; z1 = sz[old];
       FPS_TRACE(2)
     } else {
-      const int jj = j - 1;
+      const int jj = j - j_begin;
       const uint32_t bar = bar0 + 8u * (jj & 1);
       if (wid == 0) {
         // ---- 3. warp 0 folds the posts and 4a. pushes the CTA's candidate to every peer ---
@@ -243,6 +249,13 @@ fps_cluster_kernel(int n, int m, int cs, uint32_t cs_magic, int bits,
     if (rank == 0 && tid == 0) {
       idxs[j] = (int)(cs == 1 ? old : key_to_index(~old, bits));   // sampling_gpu.cu:170-171
       if (new_xyz) { new_xyz[j * 3 + 0] = x1; new_xyz[j * 3 + 1] = y1; new_xyz[j * 3 + 2] = z1; }
+    }
+  }
+  if (j_end < m) {
+#pragma unroll
+    for (int p = 0; p < P; ++p) {
+      const int k = p * t_total + g;
+      if (k < n) state_all[(size_t)scene * n + k] = td[p];
     }
   }
   if (cs > 1) cluster_sync_all();  // nobody exits while a peer may still write into it
@@ -316,10 +329,15 @@ size_t fps_smem_bytes() {
          sizeof(float) * 3 * P * kT;
 }
 
+// `exclusive`: ask for so much shared memory that no other CTA fits on the SM, so kernels that
+// run concurrently with a sampling slice do not steal issue slots from its latency chain
+constexpr size_t kExclusiveSmem = 208 * 1024;
+
 template <int P>
 cudaError_t fps_config(cudaLaunchConfig_t *cfg, cudaLaunchAttribute *attr, int b, int cs,
-                       cudaStream_t stream) {
-  const size_t smem = fps_smem_bytes<P>();
+                       cudaStream_t stream, bool exclusive = false) {
+  size_t smem = fps_smem_bytes<P>();
+  if (exclusive && smem < kExclusiveSmem) smem = kExclusiveSmem;
   cudaError_t e = cudaFuncSetAttribute(fps_cluster_kernel<P, kT>,
                                        cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
@@ -342,14 +360,14 @@ cudaError_t fps_config(cudaLaunchConfig_t *cfg, cudaLaunchAttribute *attr, int b
 }
 
 template <int P>
-int launch_fps(int b, int n, int m, int cs, int bits, const float *xyz, int *idxs, float *new_xyz,
-               cudaStream_t stream) {
+int launch_fps(int b, int n, int m, int j_begin, int j_end, int cs, int bits, const float *xyz,
+               int *idxs, float *new_xyz, float *state, bool exclusive, cudaStream_t stream) {
   cudaLaunchConfig_t cfg;
   cudaLaunchAttribute attr[1];
-  BQA_CUDA(fps_config<P>(&cfg, attr, b, cs, stream));
+  BQA_CUDA(fps_config<P>(&cfg, attr, b, cs, stream, exclusive));
   const uint32_t cs_magic = (uint32_t)((0x100000000ull + (unsigned)cs - 1) / (unsigned)cs);
-  BQA_CUDA(cudaLaunchKernelEx(&cfg, fps_cluster_kernel<P, kT>, n, m, cs, cs_magic, bits, xyz, idxs,
-                              new_xyz FPS_TRACE_PASS));
+  BQA_CUDA(cudaLaunchKernelEx(&cfg, fps_cluster_kernel<P, kT>, n, m, j_begin, j_end, cs, cs_magic, bits,
+                              xyz, idxs, new_xyz, state FPS_TRACE_PASS));
   count_launch();
   return check_launch("fps_cluster_kernel");
 }
@@ -423,8 +441,9 @@ long long fps_scratch_bytes(int b, int n) {
   return (long long)n > 16ll * kT * kMaxP ? (long long)sizeof(float) * b * n : 0;
 }
 
-int fps_dispatch(int b, int n, int m, const float *xyz, int *idxs, float *new_xyz, float *scratch,
-                 cudaStream_t stream) {
+int fps_dispatch(int b, int n, int m, int j_begin, int j_end, const float *xyz, int *idxs,
+                 float *new_xyz, float *scratch, bool exclusive, cudaStream_t stream) {
+  const bool sliced = j_begin > 1 || j_end < m;
   const int bs = ref_opt_n_threads(n);
   int bits = 0;
   while ((1 << bits) < bs) ++bits;
@@ -440,6 +459,8 @@ int fps_dispatch(int b, int n, int m, const float *xyz, int *idxs, float *new_xy
   }
   const int cs = plan.cs, per_thread = plan.per_thread;
   if (per_thread > kMaxP) {
+    if (sliced)
+      return set_error(BQA_ERR_UNSUPPORTED, "fps: n=%d is too large for sliced sampling", n);
     if (!scratch)
       return set_error(BQA_ERR_INVALID_ARG,
                        "fps: n=%d needs %lld bytes of scratch (see bqa_fps_scratch_bytes)", n,
@@ -449,7 +470,10 @@ int fps_dispatch(int b, int n, int m, const float *xyz, int *idxs, float *new_xy
     return check_launch("fps_global_kernel");
   }
   int rc = BQA_ERR_UNSUPPORTED;
-  BQA_FPS_DISPATCH(per_thread, rc = launch_fps<PP_>(b, n, m, cs, bits, xyz, idxs, new_xyz, stream));
+  if (sliced && !scratch)
+    return set_error(BQA_ERR_INVALID_ARG, "fps: sliced sampling needs a (b,n) float state buffer");
+  BQA_FPS_DISPATCH(per_thread, rc = launch_fps<PP_>(b, n, m, j_begin, j_end, cs, bits, xyz, idxs, new_xyz,
+                                                    scratch, exclusive, stream));
   return rc;
 }
 

@@ -52,7 +52,8 @@ __device__ __forceinline__ uint32_t pack2(float lo, float hi, int fp16) {
 }
 
 struct SaParams {
-  int b, n, npoint, nsample, c;     // c = feature channels (K1 = c + 3)
+  int b, n, npoint, nsample, c;     // c = feature channels (K1 = c + 3); npoint = centres in this call
+  int npoint_total, j_offset;       // the call covers centres [j_offset, j_offset + npoint) of npoint_total
   int k1pad;                        // K1 rounded up to a multiple of 16
   int feat_stride;                  // floats between consecutive points of feat_pm (>= c)
   int feat_vec4;                    // rows are 16-byte aligned: float4 loads allowed
@@ -164,13 +165,13 @@ sa_mlp_max_kernel(const SaParams P) {
     const int scene = tile / tiles_per_scene;
     const int centre0 = (tile % tiles_per_scene) * centres_per_tile;
     // this thread's row: centre j, neighbour index i
-    const int j = centre0 + tid / ns;
-    const int i = P.idx[((size_t)scene * P.npoint + j) * ns + (tid % ns)];
+    const int j = P.j_offset + centre0 + tid / ns;           // centre index in the full layout
+    const int i = P.idx[((size_t)scene * P.npoint_total + j) * ns + (tid % ns)];
     const float *frow = P.feat_pm ? P.feat_pm + ((size_t)scene * P.n + i) * P.feat_stride : nullptr;
     float rel[3];
     {
       const float *pp = P.xyz + ((size_t)scene * P.n + i) * 3;
-      const float *qq = P.new_xyz + ((size_t)scene * P.npoint + j) * 3;
+      const float *qq = P.new_xyz + ((size_t)scene * P.npoint_total + j) * 3;
 #pragma unroll
       for (int d = 0; d < 3; ++d) {
         float v = pp[d] - qq[d];                       // pointnet2_utils.py:350
@@ -298,10 +299,10 @@ sa_mlp_max_kernel(const SaParams P) {
           run = fmaxf(run, m16);
           const int col_end = c0 + g + 16;               // rows [.., col_end) folded so far
           if (col_end % ns == 0) {
-            const int jj = centre0 + col_end / ns - 1;
+            const int jj = P.j_offset + centre0 + col_end / ns - 1;
             const float o = fmaxf(run + bias, 0.f);
-            P.out_cm[((size_t)scene * C3 + ch) * P.npoint + jj] = o;
-            if (P.out_pm) P.out_pm[((size_t)scene * P.npoint + jj) * C3 + ch] = o;
+            P.out_cm[((size_t)scene * C3 + ch) * P.npoint_total + jj] = o;
+            if (P.out_pm) P.out_pm[((size_t)scene * P.npoint_total + jj) * C3 + ch] = o;
             run = -INFINITY;
           }
         }
@@ -401,13 +402,15 @@ int sa_forward_dispatch(int b, int n, int npoint, int nsample, int c, const floa
                         const float *new_xyz, const float *feat_pm, int feat_stride, const int *idx, float radius,
                         int normalize_xyz, int c1, int c2, int c3, const void *w1p, const float *b1,
                         const void *w2p, const float *b2, const void *w3p, const float *b3,
-                        float *out_cm, float *out_pm, int fp16, cudaStream_t stream) {
+                        float *out_cm, float *out_pm, int fp16, cudaStream_t stream, int npoint_total,
+                        int j_offset) {
   if (!sa_supported(nsample, npoint, c, c1, c2, c3))
     return set_error(BQA_ERR_UNSUPPORTED,
                      "sa_mlp_max: unsupported shape nsample=%d npoint=%d c=%d mlp=%d,%d,%d", nsample,
                      npoint, c, c1, c2, c3);
   SaParams P;
   P.b = b; P.n = n; P.npoint = npoint; P.nsample = nsample; P.c = c;
+  P.npoint_total = npoint_total; P.j_offset = j_offset;
   P.k1pad = (c + 3 + 15) / 16 * 16;
   P.feat_stride = feat_stride;
   P.feat_vec4 = (c % 4 == 0) && (feat_stride % 4 == 0) && ((reinterpret_cast<uintptr_t>(feat_pm) & 15) == 0);

@@ -47,7 +47,7 @@ class Pointnet2Backbone(nn.Module):
                 npoint=npoint, radius=radius, nsample=nsample, mlp=spec, use_xyz=True,
                 normalize_xyz=True))
         c = 256 * width
-        self._side_streams = {}
+        self.sa1_slices = 4      # FPS slices of SA1 whose consumers are pipelined underneath (1 = off)
         self.fp1 = PointnetFPModule(mlp=[c + c, c, c])
         self.fp2 = PointnetFPModule(mlp=[c + c, c, seed_feat_dim])
 
@@ -63,20 +63,18 @@ class Pointnet2Backbone(nn.Module):
             features._bqa_pm = pc[..., 3:].contiguous() if (c % 4 == 0 and c >= 16) else pc[..., 3:]
         return xyz, features
 
-    def _sample_all_levels(self, xyz):
-        """Inference only.  The four FPS stages depend on coordinates alone, so levels 2-4
-        (16 small CTAs, ~0.8 ms of serial latency) run on a side stream underneath SA1's
-        ball query + MLP instead of in front of SA2/3/4.  Returns [(inds, new_xyz, event)]."""
-        main = torch.cuda.current_stream(xyz.device)
-        side = self._side_streams.get(xyz.device)
-        if side is None:
-            side = self._side_streams[xyz.device] = torch.cuda.Stream(xyz.device)
-        out = [pointnet2_utils.furthest_point_sample_with_xyz(xyz, self.sa1.npoint) + (None,)]
+    def _sample_lower_levels(self, xyz1):
+        """Inference only.  The FPS stages depend on coordinates alone, so levels 2-4 (16 small
+        CTAs, ~0.6 ms of serial latency) run on a side stream underneath SA1's ball query + MLP
+        instead of in front of SA2/3/4.  Returns [(inds, new_xyz, event)] for SA2..SA4."""
+        main = torch.cuda.current_stream(xyz1.device)
+        side = fused.side_stream(xyz1.device, "fps_levels")
+        out = []
         ready = torch.cuda.Event()
         ready.record(main)
         with torch.cuda.stream(side):
             side.wait_event(ready)
-            cur = out[0][1]
+            cur = xyz1
             for sa in (self.sa2, self.sa3, self.sa4):
                 inds, new_xyz = pointnet2_utils.furthest_point_sample_with_xyz(cur, sa.npoint)
                 done = torch.cuda.Event()
@@ -93,12 +91,24 @@ class Pointnet2Backbone(nn.Module):
         overlap = (fused.enabled() and xyz.is_cuda and not self.training
                    and not torch.is_grad_enabled())
         if overlap:
-            levels = self._sample_all_levels(xyz)
             main = torch.cuda.current_stream(xyz.device)
-            outs = []
-            for sa, (inds, new_xyz, event) in zip((self.sa1, self.sa2, self.sa3, self.sa4), levels):
-                if event is not None:
-                    main.wait_event(event)
+            # SA1: sampling slices on this stream, their ball query + MLP underneath on a side
+            # stream; levels 2-4 are sampled on a second side stream as soon as SA1's centres exist
+            piped = self.sa1.forward_pipelined(xyz, features, slices=self.sa1_slices)
+            if piped is not None:
+                xyz1, feats1, inds1, done1 = piped
+            else:
+                inds1, xyz1 = pointnet2_utils.furthest_point_sample_with_xyz(xyz, self.sa1.npoint)
+                done1 = None
+            levels = self._sample_lower_levels(xyz1)
+            if piped is None:
+                xyz1, feats1, inds1 = self.sa1(xyz, features, inds1, new_xyz=xyz1)
+            else:
+                main.wait_event(done1)
+            outs = [(xyz1, feats1, inds1)]
+            xyz, features = xyz1, feats1
+            for sa, (inds, new_xyz, event) in zip((self.sa2, self.sa3, self.sa4), levels):
+                main.wait_event(event)
                 xyz, features, inds = sa(xyz, features, inds, new_xyz=new_xyz)
                 outs.append((xyz, features, inds))
         else:

@@ -143,6 +143,24 @@ class PointnetSAModuleVotes(nn.Module):
         self._fused_cache = None       # folded weights are stale once BN stats can move
         return super().train(mode)
 
+    def _packed(self):
+        sig = fused.weights_signature(self.mlp_module)
+        if self._fused_cache is None or self._fused_cache[0] != sig:
+            self._fused_cache = (sig, fused.fold_sa_mlp(self.mlp_module))
+        return self._fused_cache[1]
+
+    def forward_pipelined(self, xyz, features=None, slices=4):
+        """Inference only: FPS in resumable slices with ball query + fused MLP of each slice's
+        centres running underneath the next slice (fused.sa_forward_pipelined).  Returns
+        (new_xyz, new_features, inds, done_event) or None when the layer cannot take this path."""
+        if not (self._can_fuse(xyz, features) and self.npoint % slices == 0
+                and (self.npoint // slices * self.nsample) % 128 == 0):
+            return None
+        inds, new_xyz, feats, done = fused.sa_forward_pipelined(
+            xyz, features, self.npoint, self.radius, self.nsample, self.normalize_xyz, self._packed(),
+            slices)
+        return new_xyz, feats, inds, done
+
     def forward(self, xyz, features=None, inds=None, new_xyz=None):
         """`new_xyz` (optional, beyond the reference signature): the centres xyz[inds] when the
         caller already has them (e.g. from the FPS kernel's epilogue), skipping the gather."""
@@ -154,11 +172,8 @@ class PointnetSAModuleVotes(nn.Module):
             inds, new_xyz = _centres(xyz, self.npoint, inds)
 
         if self._can_fuse(xyz, features):
-            sig = fused.weights_signature(self.mlp_module)
-            if self._fused_cache is None or self._fused_cache[0] != sig:
-                self._fused_cache = (sig, fused.fold_sa_mlp(self.mlp_module))
             new_features = fused.sa_forward(xyz, new_xyz, features, self.radius, self.nsample,
-                                            self.normalize_xyz, self._fused_cache[1])
+                                            self.normalize_xyz, self._packed())
             return new_xyz, new_features, inds
 
         grouped = self.grouper(xyz, new_xyz, features)

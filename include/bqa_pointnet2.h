@@ -54,6 +54,15 @@ BQA_API long long bqa_fps_scratch_bytes(int b, int n);
 BQA_API int bqa_furthest_point_sampling(int b, int n, int m, const float *xyz, int *idxs,
                                 float *new_xyz, float *scratch, void *stream);
 
+/* Sliced sampling: produce samples j_begin .. j_end-1 only (1 <= j_begin <= j_end <= m; sample 0
+ * is written by the slice with j_begin == 1).  Slices must be issued in order on one stream; the
+ * running min-distances travel between them in `state` (b,n) f32.  Results are identical to one
+ * full call.  Lets consumers of the first centres (ball query, SA MLP) run on another stream
+ * underneath the later slices.  exclusive != 0 keeps other kernels off the SMs a slice runs on. */
+BQA_API int bqa_furthest_point_sampling_slice(int b, int n, int m, int j_begin, int j_end,
+                                              const float *xyz, int *idxs, float *new_xyz,
+                                              float *state, int exclusive, void *stream);
+
 /* ---- gather -------------------------------------------------------------------
  * replaces: gather_points / gather_points_grad, src/sampling.cpp:15-65,
  *           kernels src/sampling_gpu.cu:8-57.
@@ -75,6 +84,13 @@ BQA_API int bqa_gather_points_grad(int b, int c, int n, int m, const float *grad
 BQA_API long long bqa_ball_query_workspace_bytes(int b, int n, int m, int nsample);
 BQA_API int bqa_ball_query(int b, int n, int m, float radius, int nsample, const float *new_xyz,
                    const float *xyz, int *idx, void *workspace, void *stream);
+
+/* Slice form: only the centres [j_begin, j_begin + j_count) of each scene's m_total centres are
+ * queried; new_xyz (b,m_total,3) and idx (b,m_total,nsample) keep their full-size layout.  The
+ * workspace is sized for (b, n, j_count, nsample). */
+BQA_API int bqa_ball_query_slice(int b, int n, int m_total, int j_begin, int j_count, float radius,
+                                 int nsample, const float *new_xyz, const float *xyz, int *idx,
+                                 void *workspace, void *stream);
 
 /* ---- grouping -----------------------------------------------------------------
  * replaces: group_points / group_points_grad, src/group_points.cpp:12-62,
@@ -134,6 +150,17 @@ BQA_API int bqa_sa_mlp_max_forward(int b, int n, int npoint, int nsample, int c,
                                    const void *w1p, const float *b1, const void *w2p,
                                    const float *b2, const void *w3p, const float *b3,
                                    float *out_cm, float *out_pm, int precision, void *stream);
+
+/* Slice form: only the centres [j_begin, j_begin + j_count) of each scene's npoint_total centres
+ * are processed; new_xyz, idx, out_cm and out_pm keep their full-size layouts (j_count * nsample
+ * must be a multiple of 128). */
+BQA_API int bqa_sa_mlp_max_forward_slice(int b, int n, int npoint_total, int j_begin, int j_count,
+                                         int nsample, int c, const float *xyz, const float *new_xyz,
+                                         const float *feat_pm, int feat_stride, const int *idx,
+                                         float radius, int normalize_xyz, int c1, int c2, int c3,
+                                         const void *w1p, const float *b1, const void *w2p,
+                                         const float *b2, const void *w3p, const float *b3,
+                                         float *out_cm, float *out_pm, int precision, void *stream);
 
 /* ---- fused feature-propagation layer (inference) -----------------------------------
  * replaces PointnetFPModule.forward (pointnet2_modules.py:376-421): three_nn ->

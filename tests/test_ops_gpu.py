@@ -308,3 +308,38 @@ def test_ops_run_on_current_stream_and_count_launches():
     s.synchronize()
     assert _native.launch_count() == before + 1
     assert torch.equal(a, ext.furthest_point_sampling(x, 128))
+
+
+# ------------------------------------------------------------------ slice forms ---
+
+@pytest.mark.parametrize("b,n,m,cuts", [(3, 40000, 512, [1, 100, 101, 400, 512]), (2, 3000, 300, [1, 150, 300]),
+                                        (2, 20000, 256, [1, 64, 128, 192, 256])])
+def test_fps_slices_equal_one_call(b, n, m, cuts):
+    """Sliced (resumable) sampling produces exactly the indices / centres of one full call."""
+    import ctypes
+    from bridgeqa_b200 import _native as N
+    xyz = dev(scenes(b, n, first=13))
+    want, want_xyz = ext.furthest_point_sampling(xyz, m, return_xyz=True)
+    inds = torch.full((b, m), -1, dtype=torch.int32, device="cuda")
+    new_xyz = torch.zeros((b, m, 3), device="cuda")
+    state = torch.empty((b, n), device="cuda")
+    for lo, hi in zip(cuts[:-1], cuts[1:]):
+        N.call("bqa_furthest_point_sampling_slice", b, n, m, lo, hi, N.ptr(xyz), N.ptr(inds), N.ptr(new_xyz),
+               N.ptr(state), 1, N.stream_ptr(xyz.device))
+    assert torch.equal(inds, want) and torch.equal(new_xyz, want_xyz)
+
+
+def test_ball_query_slices_equal_one_call():
+    import ctypes
+    from bridgeqa_b200 import _native as N
+    b, n, m, ns, r = 2, 20000, 512, 32, 0.25
+    xyz = dev(scenes(b, n, first=17))
+    _, centres = ext.furthest_point_sampling(xyz, m, return_xyz=True)
+    want = ext.ball_query(centres, xyz, r, ns)
+    idx = torch.full((b, m, ns), -1, dtype=torch.int32, device="cuda")
+    for lo, cnt in [(0, 128), (128, 256), (384, 128)]:
+        nbytes = N.lib().bqa_ball_query_workspace_bytes(b, n, cnt, ns)
+        work = torch.empty((max(nbytes, 1),), dtype=torch.uint8, device="cuda")
+        N.call("bqa_ball_query_slice", b, n, m, lo, cnt, ctypes.c_float(r), ns, N.ptr(centres), N.ptr(xyz),
+               N.ptr(idx), N.ptr(work) if nbytes else ctypes.c_void_p(0), N.stream_ptr(xyz.device))
+    assert torch.equal(idx, want)

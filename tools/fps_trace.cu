@@ -31,7 +31,7 @@ int main(int argc, char **argv) {
     cudaMemset(trace, 0, 64 * 8);
     cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
     cudaEventRecord(e0);
-    int rc = bqa::fps_dispatch(b, n, m, xyz, idx, nx, nullptr, 0);
+    int rc = bqa::fps_dispatch(b, n, m, 1, m, xyz, idx, nx, nullptr, false, 0);
     cudaEventRecord(e1); cudaEventSynchronize(e1);
     float ms; cudaEventElapsedTime(&ms, e0, e1);
     unsigned long long t[64]; cudaMemcpy(t, trace, sizeof(t), cudaMemcpyDeviceToHost);
