@@ -47,7 +47,11 @@ class Pointnet2Backbone(nn.Module):
                 npoint=npoint, radius=radius, nsample=nsample, mlp=spec, use_xyz=True,
                 normalize_xyz=True))
         c = 256 * width
-        self.sa1_slices = 4      # FPS slices of SA1 whose consumers are pipelined underneath (1 = off)
+        # FPS slices of SA1 whose ball query + MLP are pipelined underneath (1 = off, the default:
+        # measured slower on B200) -- developer knobs
+        import os
+        self.sa1_slices = int(os.environ.get("BQA_SA1_SLICES", "1"))
+        self.sa1_exclusive = os.environ.get("BQA_FPS_EXCLUSIVE", "1") != "0"
         self.fp1 = PointnetFPModule(mlp=[c + c, c, c])
         self.fp2 = PointnetFPModule(mlp=[c + c, c, seed_feat_dim])
 
@@ -94,7 +98,9 @@ class Pointnet2Backbone(nn.Module):
             main = torch.cuda.current_stream(xyz.device)
             # SA1: sampling slices on this stream, their ball query + MLP underneath on a side
             # stream; levels 2-4 are sampled on a second side stream as soon as SA1's centres exist
-            piped = self.sa1.forward_pipelined(xyz, features, slices=self.sa1_slices)
+            piped = (self.sa1.forward_pipelined(xyz, features, slices=self.sa1_slices,
+                                                exclusive=self.sa1_exclusive)
+                     if self.sa1_slices > 1 else None)
             if piped is not None:
                 xyz1, feats1, inds1, done1 = piped
             else:

@@ -196,7 +196,8 @@ def side_stream(device, tag):
     return _side_streams[key]
 
 
-def sa_forward_pipelined(xyz, features, npoint, radius, nsample, normalize_xyz, packed, slices=4):
+def sa_forward_pipelined(xyz, features, npoint, radius, nsample, normalize_xyz, packed, slices=4,
+                         exclusive=True):
     """Sampling + grouping + MLP of one SA layer as a software pipeline: the furthest point
     sampling is issued in `slices` resumable slices on the current stream, and the ball query +
     fused MLP of the centres a slice produced run on a side stream underneath the following
@@ -232,7 +233,7 @@ def sa_forward_pipelined(xyz, features, npoint, radius, nsample, normalize_xyz, 
         for k in range(slices):
             lo, hi = bounds[k], bounds[k + 1]
             N.call("bqa_furthest_point_sampling_slice", b, n, m, max(lo, 1), hi, N.ptr(xyz), N.ptr(inds),
-                   N.ptr(new_xyz), N.ptr(state), 1, N.stream_ptr(dev))
+                   N.ptr(new_xyz), N.ptr(state), 1 if exclusive else 0, N.stream_ptr(dev))
             sampled = torch.cuda.Event()
             sampled.record(main)
             with torch.cuda.stream(side):
