@@ -27,11 +27,16 @@ _SIGNATURES = {
     "bqa_fps_scratch_bytes": ([_I, _I], _LL),
     "bqa_furthest_point_sampling": ([_I, _I, _I, _P, _P, _P, _P, _P], _I),
     "bqa_furthest_point_sampling_slice": ([_I, _I, _I, _I, _I, _P, _P, _P, _P, _I, _P], _I),
+    "bqa_fps_prefix_check": ([_I, _I, _I, _P, _P, _P, _P], _I),
+    "bqa_furthest_point_sampling_cond": ([_I, _I, _I, _P, _P, _P, _P, _P, _P], _I),
     "bqa_gather_points": ([_I, _I, _I, _I, _P, _P, _P, _P], _I),
     "bqa_gather_points_grad": ([_I, _I, _I, _I, _P, _P, _P, _P], _I),
     "bqa_ball_query_workspace_bytes": ([_I, _I, _I, _I], _LL),
     "bqa_ball_query": ([_I, _I, _I, _F, _I, _P, _P, _P, _P, _P], _I),
     "bqa_ball_query_slice": ([_I, _I, _I, _I, _I, _F, _I, _P, _P, _P, _P, _P], _I),
+    "bqa_ball_query_grid_bytes": ([_I, _I], _LL),
+    "bqa_ball_query_grid_build": ([_I, _I, _F, _P, _P, _P], _I),
+    "bqa_ball_query_grid_search": ([_I, _I, _I, _I, _I, _F, _I, _P, _P, _P, _P, _P], _I),
     "bqa_group_points": ([_I, _I, _I, _I, _I, _P, _P, _P, _P], _I),
     "bqa_group_points_grad": ([_I, _I, _I, _I, _I, _P, _P, _P, _P], _I),
     "bqa_three_nn": ([_I, _I, _I, _P, _P, _P, _P, _P], _I),

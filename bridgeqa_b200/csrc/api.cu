@@ -41,12 +41,23 @@ int ref_opt_n_threads(int work_size) {
 
 // dispatchers implemented in the kernel translation units
 int fps_dispatch(int b, int n, int m, int j_begin, int j_end, const float *xyz, int *idxs,
-                 float *new_xyz, float *scratch, bool exclusive, cudaStream_t stream);
+                 float *new_xyz, float *scratch, bool exclusive, const int *run_flags,
+                 cudaStream_t stream);
+bool fps_prefix_check_supported(int n, int m);
+int fps_prefix_check_dispatch(int b, int n, int m, const float *xyz, float *v_scratch, int *run_flags,
+                              cudaStream_t stream);
+int fps_identity_fill_dispatch(int b, int n, int m, const float *xyz, const int *run_flags, int *idxs,
+                               float *new_xyz, cudaStream_t stream);
 long long fps_scratch_bytes(int b, int n);
 int ball_query_dispatch(int b, int n, int m, float radius, int nsample, const float *new_xyz,
                         const float *xyz, int *idx, void *workspace, cudaStream_t stream,
                         int q_stride, int q_offset);
 long long ball_query_workspace_bytes(int b, int n, int m, int nsample);
+long long ball_query_grid_bytes(int b, int n);
+int ball_query_grid_build(int b, int n, float radius, const float *xyz, void *grid, cudaStream_t stream);
+int ball_query_grid_search(int b, int n, int m, float radius, int nsample, const float *new_xyz,
+                           const float *xyz, int *idx, const void *grid, cudaStream_t stream,
+                           int q_stride, int q_offset);
 int gather_rows_dispatch(int b, int c, int n, long long e_total, const float *points, const int *idx,
                          float *out, cudaStream_t stream);
 int scatter_add_rows_dispatch(int b, int c, int n, long long e_total, const float *grad_out,
@@ -97,7 +108,29 @@ int bqa_furthest_point_sampling(int b, int n, int m, const float *xyz, int *idxs
   if (b == 0 || m == 0) return BQA_OK;
   BQA_REQUIRE(n > 0, "%s: n must be > 0 when m > 0", __func__);
   PTR(xyz); PTR(idxs);
-  return fps_dispatch(b, n, m, 1, m, xyz, idxs, new_xyz, scratch, false, (cudaStream_t)stream);
+  return fps_dispatch(b, n, m, 1, m, xyz, idxs, new_xyz, scratch, false, nullptr, (cudaStream_t)stream);
+}
+
+int bqa_fps_prefix_check(int b, int n, int m, const float *xyz, float *v_scratch, int *run_flags,
+                         void *stream) {
+  NONNEG(b); NONNEG(n); NONNEG(m);
+  if (b == 0) return BQA_OK;
+  PTR(run_flags);
+  BQA_REQUIRE(fps_prefix_check_supported(n, m), "%s: need 1 <= m <= min(n, 8192), got n=%d m=%d",
+              __func__, n, m);
+  PTR(xyz); PTR(v_scratch);
+  return fps_prefix_check_dispatch(b, n, m, xyz, v_scratch, run_flags, (cudaStream_t)stream);
+}
+
+int bqa_furthest_point_sampling_cond(int b, int n, int m, const float *xyz, const int *run_flags,
+                                     int *idxs, float *new_xyz, float *scratch, void *stream) {
+  NONNEG(b); NONNEG(n); NONNEG(m);
+  if (b == 0 || m == 0) return BQA_OK;
+  BQA_REQUIRE(n > 0 && m <= n, "%s: need 0 < m <= n", __func__);
+  PTR(xyz); PTR(idxs); PTR(run_flags);
+  if (int rc = fps_identity_fill_dispatch(b, n, m, xyz, run_flags, idxs, new_xyz, (cudaStream_t)stream))
+    return rc;
+  return fps_dispatch(b, n, m, 1, m, xyz, idxs, new_xyz, scratch, false, run_flags, (cudaStream_t)stream);
 }
 
 int bqa_furthest_point_sampling_slice(int b, int n, int m, int j_begin, int j_end, const float *xyz,
@@ -108,7 +141,7 @@ int bqa_furthest_point_sampling_slice(int b, int n, int m, int j_begin, int j_en
   if (b == 0 || m == 0) return BQA_OK;
   BQA_REQUIRE(n > 0, "%s: n must be > 0 when m > 0", __func__);
   PTR(xyz); PTR(idxs);
-  return fps_dispatch(b, n, m, j_begin, j_end, xyz, idxs, new_xyz, state, exclusive != 0,
+  return fps_dispatch(b, n, m, j_begin, j_end, xyz, idxs, new_xyz, state, exclusive != 0, nullptr,
                       (cudaStream_t)stream);
 }
 
@@ -155,6 +188,32 @@ int bqa_ball_query_slice(int b, int n, int m_total, int j_begin, int j_count, fl
   if (n > 0) PTR(xyz);
   return ball_query_dispatch(b, n, j_count, radius, nsample, new_xyz, xyz, idx, workspace,
                              (cudaStream_t)stream, m_total, j_begin);
+}
+
+long long bqa_ball_query_grid_bytes(int b, int n) {
+  if (b <= 0 || n <= 0) return 0;
+  return ball_query_grid_bytes(b, n);
+}
+
+int bqa_ball_query_grid_build(int b, int n, float radius, const float *xyz, void *grid, void *stream) {
+  NONNEG(b); NONNEG(n);
+  if ((long long)b * n == 0) return BQA_OK;
+  PTR(xyz); PTR(grid);
+  return ball_query_grid_build(b, n, radius, xyz, grid, (cudaStream_t)stream);
+}
+
+int bqa_ball_query_grid_search(int b, int n, int m_total, int j_begin, int j_count, float radius,
+                               int nsample, const float *new_xyz, const float *xyz, int *idx,
+                               const void *grid, void *stream) {
+  NONNEG(b); NONNEG(n); NONNEG(m_total); NONNEG(nsample);
+  BQA_REQUIRE(j_begin >= 0 && j_count >= 0 && j_begin + j_count <= m_total,
+              "%s: slice [%d, %d) outside [0, %d)", __func__, j_begin, j_begin + j_count, m_total);
+  if ((long long)b * j_count * nsample == 0) return BQA_OK;
+  PTR(new_xyz); PTR(idx);
+  BQA_REQUIRE(n > 0, "%s: a grid needs at least one point", __func__);
+  PTR(xyz); PTR(grid);
+  return ball_query_grid_search(b, n, j_count, radius, nsample, new_xyz, xyz, idx, grid,
+                                (cudaStream_t)stream, m_total, j_begin);
 }
 
 int bqa_group_points(int b, int c, int n, int npoints, int nsample, const float *points,

@@ -19,12 +19,8 @@
 // nsample hits in ascending index", applies the reference's back-fill with the first hit
 // and writes the rows coalesced.
 //
-// Queries are handed to threads in ascending x (a per-scene bitonic sort of the m centres),
-// so the 32 queries of a warp lie in a thin x-slab and one |dx| test per point -- 4 FADD,
-// two |.|-FMNMX and one compare per 4 points -- rejects ~93 % of the points for the whole
-// warp before the exact 3-D distance is evaluated.  The filter is conservative
-// (|dx| >= r(1+1e-6) implies fl(dx*dx) >= r*r, and the exact d2 >= fl(dx*dx) because the
-// other two terms are non-negative and rounding is monotone), so the hit set is unchanged.
+// Scenes of >= kGridMinPoints points (with a workspace) do not come here at all: they are
+// binned into a cell grid and searched by ball_query_grid.cu.
 //
 // Bit-exact: d2 = fma(dz,dz,fma(dx,dx,dy*dy)) (nvcc's contraction of
 // ball_query_gpu.cu:30-31), compared `<` against radius*radius computed in fp32.
@@ -47,50 +43,14 @@ __device__ __forceinline__ void bulk_load(uint32_t dst, const void *src, uint32_
       : "memory");
 }
 
-struct BqWorkspace {       // carved out of the caller's workspace
-  int *perm;               // [b * m]  queries in ascending x (NULL: identity)
+struct BqWorkspace {       // carved out of the caller's workspace when S > 1
   unsigned int *ticket;    // [b * qblocks]   zeroed by the dispatcher (S > 1)
   int *count;              // [b * m * S]
   int *hits;               // [b * m * S * nsample]
 };
 
-constexpr int kSortMax = 4096;     // centres per scene the shared-memory sort handles
-
-// one CTA per scene: perm = argsort(new_xyz[:, 0]) (ties by index), bitonic in shared memory
-__global__ void __launch_bounds__(1024)
-sort_queries_kernel(int m, int q_stride, int q_offset, const float *__restrict__ new_xyz_all,
-                    int *__restrict__ perm_all) {
-  __shared__ unsigned long long keys[kSortMax];
-  const int scene = blockIdx.x;
-  int npow = 1;
-  while (npow < m) npow <<= 1;
-  for (int i = threadIdx.x; i < npow; i += blockDim.x) {
-    unsigned long long k = ~0ull;
-    if (i < m) {
-      const uint32_t u = __float_as_uint(new_xyz_all[((size_t)scene * q_stride + q_offset + i) * 3]);
-      const uint32_t ord = (u & 0x80000000u) ? ~u : (u | 0x80000000u);     // float order -> uint order
-      k = ((unsigned long long)ord << 32) | (uint32_t)i;
-    }
-    keys[i] = k;
-  }
-  __syncthreads();
-  for (int size = 2; size <= npow; size <<= 1) {
-    for (int stride = size >> 1; stride > 0; stride >>= 1) {
-      for (int i = threadIdx.x; i < npow / 2; i += blockDim.x) {
-        const int lo = 2 * i - (i & (stride - 1));
-        const int hi = lo + stride;
-        const bool up = (lo & size) == 0;
-        const unsigned long long a = keys[lo], c = keys[hi];
-        if ((a > c) == up) { keys[lo] = c; keys[hi] = a; }
-      }
-      __syncthreads();
-    }
-  }
-  for (int i = threadIdx.x; i < m; i += blockDim.x) perm_all[(size_t)scene * m + i] = (int)(uint32_t)keys[i];
-}
-
 __global__ void __launch_bounds__(kQueries)
-ball_query_kernel(int n, int m, int q_stride, int q_offset, float radius2, float rfilt, int nsample,
+ball_query_kernel(int n, int m, int q_stride, int q_offset, float radius2, int nsample,
                   int nseg, int seg_len,
                   const float *__restrict__ new_xyz_all, const float *__restrict__ xyz_all,
                   int *__restrict__ idx_all, BqWorkspace ws) {
@@ -101,10 +61,9 @@ ball_query_kernel(int n, int m, int q_stride, int q_offset, float radius2, float
   const int tid = threadIdx.x;
   const int scene = blockIdx.z;
   const int seg = blockIdx.y;
-  const int slot = blockIdx.x * kQueries + tid;
+  const int j = blockIdx.x * kQueries + tid;
   const float *xyz = xyz_all + (size_t)scene * n * 3;
-  const bool live = slot < m;
-  const int j = (live && ws.perm) ? ws.perm[(size_t)scene * m + slot] : slot;
+  const bool live = j < m;
   const int k_begin = seg * seg_len;
   const int k_end = min(n, k_begin + seg_len);
 
@@ -183,16 +142,14 @@ ball_query_kernel(int n, int m, int q_stride, int q_offset, float radius2, float
 #pragma unroll 2
       for (int g = 0; g < tn / 4; ++g) {
         const float4 a = t4[3 * g], bq = t4[3 * g + 1], c = t4[3 * g + 2];
-        // x-slab filter (conservative, see the header): most groups end here for the whole warp;
-        // behind it each point is re-tested on its own so the exact distance is only evaluated
-        // for the ~1 in 4 points of a passing group that can actually be inside the ball
-        const float e0 = fabsf(qx - a.x), e1 = fabsf(qx - a.w), e2 = fabsf(qx - bq.z), e3 = fabsf(qx - c.y);
-        if (!(fminf(fminf(e0, e1), fminf(e2, e3)) < rfilt)) continue;
-        const int k = kbase + 4 * g;
-        if (e0 < rfilt) hit(sqdist3(qx, qy, qz, a.x, a.y, a.z), k);
-        if (e1 < rfilt) hit(sqdist3(qx, qy, qz, a.w, bq.x, bq.y), k + 1);
-        if (e2 < rfilt) hit(sqdist3(qx, qy, qz, bq.z, bq.w, c.x), k + 2);
-        if (e3 < rfilt) hit(sqdist3(qx, qy, qz, c.y, c.z, c.w), k + 3);
+        const float d0 = sqdist3(qx, qy, qz, a.x, a.y, a.z);
+        const float d1 = sqdist3(qx, qy, qz, a.w, bq.x, bq.y);
+        const float d2 = sqdist3(qx, qy, qz, bq.z, bq.w, c.x);
+        const float d3 = sqdist3(qx, qy, qz, c.y, c.z, c.w);
+        if (fminf(fminf(d0, d1), fminf(d2, d3)) < radius2) {
+          const int k = kbase + 4 * g;
+          hit(d0, k); hit(d1, k + 1); hit(d2, k + 2); hit(d3, k + 3);
+        }
       }
     }
     __syncthreads();  // everyone is done with stage s
@@ -225,7 +182,7 @@ ball_query_kernel(int n, int m, int q_stride, int q_offset, float radius2, float
   const int nq = min(kQueries, m - q0);
   for (int e = tid; e < nq * nsample; e += kQueries) {      // consecutive threads = consecutive slots
     const int q = e / nsample, slot = e - q * nsample;
-    const int jq = ws.perm ? __ldg(&ws.perm[(size_t)scene * m + q0 + q]) : q0 + q;
+    const int jq = q0 + q;
     const size_t ql = ((size_t)scene * m + jq) * nseg;
     int remaining = slot, value = 0, first_hit = 0;
     bool found = false, seen = false;
@@ -253,36 +210,38 @@ int plan_segments(int b, int n, int m) {
 long long ticket_bytes(int b, int m) {
   return ((long long)b * ceil_div(m, kQueries) * 4 + 255) / 256 * 256;
 }
-long long perm_bytes(int b, int m) { return ((long long)b * m * 4 + 255) / 256 * 256; }
-// sorting pays off once the scan is long enough to amortise the extra launch
-bool want_sort(int n, int m) { return m >= 64 && m <= kSortMax && n >= 4096; }
 
 }  // namespace
 
+// ball_query_grid.cu
+long long ball_query_grid_bytes(int b, int n);
+bool ball_query_grid_wanted(int n, int m);
+int ball_query_grid_build(int b, int n, float radius, const float *xyz, void *grid, cudaStream_t stream);
+int ball_query_grid_search(int b, int n, int m, float radius, int nsample, const float *new_xyz,
+                           const float *xyz, int *idx, const void *grid, cudaStream_t stream,
+                           int q_stride, int q_offset);
+
 long long ball_query_workspace_bytes(int b, int n, int m, int nsample) {
+  if (ball_query_grid_wanted(n, m)) return ball_query_grid_bytes(b, n);
   const int s = plan_segments(b, n, m);
-  long long bytes = want_sort(n, m) ? perm_bytes(b, m) : 0;
-  if (s > 1) bytes += ticket_bytes(b, m) + 4ll * b * m * s + 4ll * b * m * s * nsample;
-  return bytes;
+  if (s == 1) return 0;
+  return ticket_bytes(b, m) + 4ll * b * m * s + 4ll * b * m * s * nsample;
 }
 
 int ball_query_dispatch(int b, int n, int m, float radius, int nsample, const float *new_xyz,
                         const float *xyz, int *idx, void *workspace, cudaStream_t stream,
                         int q_stride, int q_offset) {
+  if (workspace && ball_query_grid_wanted(n, m)) {
+    // large scene: bin once, then a warp per query over the cells its ball touches
+    if (int rc = ball_query_grid_build(b, n, radius, xyz, workspace, stream)) return rc;
+    return ball_query_grid_search(b, n, m, radius, nsample, new_xyz, xyz, idx, workspace, stream,
+                                  q_stride, q_offset);
+  }
   const float radius2 = radius * radius;  // ball_query_gpu.cu:21, fp32 product
   const int nseg = workspace ? plan_segments(b, n, m) : 1;
-  BqWorkspace ws = {nullptr, nullptr, nullptr, nullptr};
+  BqWorkspace ws = {nullptr, nullptr, nullptr};
   int seg_len = n;
   char *wsp = reinterpret_cast<char *>(workspace);
-  if (workspace && want_sort(n, m)) {
-    ws.perm = reinterpret_cast<int *>(wsp);
-    wsp += perm_bytes(b, m);
-    sort_queries_kernel<<<b, 1024, 0, stream>>>(m, q_stride, q_offset, new_xyz, ws.perm);
-    count_launch();
-    if (int rc = check_launch("sort_queries_kernel")) return rc;
-  }
-  // |dx| >= rfilt  =>  fl(dx*dx) >= radius2  (1e-6 relative margin, rounded up)
-  const float rfilt = nextafterf((float)(sqrt((double)radius2) * (1.0 + 1e-6)), INFINITY);
   if (nseg > 1) {
     const long long tickets = ticket_bytes(b, m);
     ws.ticket = reinterpret_cast<unsigned int *>(wsp);
@@ -293,7 +252,7 @@ int ball_query_dispatch(int b, int n, int m, float radius, int nsample, const fl
   }
   if (b > 65535) return set_error(BQA_ERR_UNSUPPORTED, "ball_query: batch too large");
   dim3 grid((unsigned)ceil_div(m, kQueries), (unsigned)nseg, (unsigned)b);
-  ball_query_kernel<<<grid, kQueries, 0, stream>>>(n, m, q_stride, q_offset, radius2, rfilt, nsample, nseg,
+  ball_query_kernel<<<grid, kQueries, 0, stream>>>(n, m, q_stride, q_offset, radius2, nsample, nseg,
                                                    seg_len, new_xyz, xyz, idx, ws);
   count_launch();
   return check_launch("ball_query_kernel");

@@ -105,7 +105,11 @@ template <int P, int T>
 __global__ void __launch_bounds__(T, 1)
 fps_cluster_kernel(int n, int m, int j_begin, int j_end, int cs, uint32_t cs_magic, int bits,
                    const float *__restrict__ xyz_all, int *__restrict__ idx_all,
-                   float *__restrict__ new_xyz_all, float *__restrict__ state_all FPS_TRACE_ARG) {
+                   float *__restrict__ new_xyz_all, float *__restrict__ state_all,
+                   const int *__restrict__ run_flags FPS_TRACE_ARG) {
+  // run_flags (optional): scenes whose flag is 0 already hold their answer (the identity prefix,
+  // see fps_prefix_check_kernel) -- the whole cluster leaves before touching any barrier.
+  if (run_flags && run_flags[blockIdx.x / cs] == 0) return;
   // Samples j_begin .. j_end-1 are produced by this launch (1 <= j_begin <= j_end <= m).  A
   // launch that does not start at 1 resumes from the running min-distances a previous launch
   // left in state_all (b,n), one that does not end at m leaves them there: the sampling can be
@@ -267,9 +271,10 @@ fps_cluster_kernel(int n, int m, int j_begin, int j_end, int cs, uint32_t cs_mag
 __global__ void __launch_bounds__(1024, 1)
 fps_global_kernel(int n, int m, int bits, const float *__restrict__ xyz_all,
                   float *__restrict__ temp_all, int *__restrict__ idx_all,
-                  float *__restrict__ new_xyz_all) {
+                  float *__restrict__ new_xyz_all, const int *__restrict__ run_flags) {
   __shared__ uint2 part[32];
   __shared__ uint32_t winner;
+  if (run_flags && run_flags[blockIdx.x] == 0) return;
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const int scene = blockIdx.x;
   const float *xyz = xyz_all + (size_t)scene * n * 3;
@@ -361,13 +366,14 @@ cudaError_t fps_config(cudaLaunchConfig_t *cfg, cudaLaunchAttribute *attr, int b
 
 template <int P>
 int launch_fps(int b, int n, int m, int j_begin, int j_end, int cs, int bits, const float *xyz,
-               int *idxs, float *new_xyz, float *state, bool exclusive, cudaStream_t stream) {
+               int *idxs, float *new_xyz, float *state, bool exclusive, const int *run_flags,
+               cudaStream_t stream) {
   cudaLaunchConfig_t cfg;
   cudaLaunchAttribute attr[1];
   BQA_CUDA(fps_config<P>(&cfg, attr, b, cs, stream, exclusive));
   const uint32_t cs_magic = (uint32_t)((0x100000000ull + (unsigned)cs - 1) / (unsigned)cs);
   BQA_CUDA(cudaLaunchKernelEx(&cfg, fps_cluster_kernel<P, kT>, n, m, j_begin, j_end, cs, cs_magic, bits,
-                              xyz, idxs, new_xyz, state FPS_TRACE_PASS));
+                              xyz, idxs, new_xyz, state, run_flags FPS_TRACE_PASS));
   count_launch();
   return check_launch("fps_cluster_kernel");
 }
@@ -442,7 +448,8 @@ long long fps_scratch_bytes(int b, int n) {
 }
 
 int fps_dispatch(int b, int n, int m, int j_begin, int j_end, const float *xyz, int *idxs,
-                 float *new_xyz, float *scratch, bool exclusive, cudaStream_t stream) {
+                 float *new_xyz, float *scratch, bool exclusive, const int *run_flags,
+                 cudaStream_t stream) {
   const bool sliced = j_begin > 1 || j_end < m;
   const int bs = ref_opt_n_threads(n);
   int bits = 0;
@@ -465,7 +472,7 @@ int fps_dispatch(int b, int n, int m, int j_begin, int j_end, const float *xyz, 
       return set_error(BQA_ERR_INVALID_ARG,
                        "fps: n=%d needs %lld bytes of scratch (see bqa_fps_scratch_bytes)", n,
                        (long long)sizeof(float) * b * n);
-    fps_global_kernel<<<b, 1024, 0, stream>>>(n, m, bits, xyz, scratch, idxs, new_xyz);
+    fps_global_kernel<<<b, 1024, 0, stream>>>(n, m, bits, xyz, scratch, idxs, new_xyz, run_flags);
     count_launch();
     return check_launch("fps_global_kernel");
   }
@@ -473,8 +480,108 @@ int fps_dispatch(int b, int n, int m, int j_begin, int j_end, const float *xyz, 
   if (sliced && !scratch)
     return set_error(BQA_ERR_INVALID_ARG, "fps: sliced sampling needs a (b,n) float state buffer");
   BQA_FPS_DISPATCH(per_thread, rc = launch_fps<PP_>(b, n, m, j_begin, j_end, cs, bits, xyz, idxs, new_xyz,
-                                                    scratch, exclusive, stream));
+                                                    scratch, exclusive, run_flags, stream));
   return rc;
+}
+
+// ---- sampling a cloud that is itself in sampling order -------------------------------------
+//
+// SA2-4 sample the centres the previous level sampled (models/backbone_module.py:52-86), i.e. a
+// cloud already in furthest-point order.  Re-sampling such a cloud returns the prefix
+// 0,1,...,m-1 -- the reference's own comment says so (backbone_module.py:111) -- unless two
+// candidates tie, and then the reference's tie-break decides.  The serial chain (m-1 dependent
+// argmax steps, 0.7 ms for the three levels) can therefore be replaced by a PARALLEL proof:
+//   V[j]    = min(1e10, min_{i<j} d(x_j, x_i))        what the chain would hold for point j at step j
+//   R(k, j) = min(1e10, min_{i<j} d(x_k, x_i))        ... and for any later point k
+// If V[j] > 0 and R(k, j) < V[j] STRICTLY for every j in [1, m) and every k in (j, n), and no
+// point k >= 1 is in the reference's skip set (|x|^2 <= 1e-3), then at every step point j is the
+// unique maximum (earlier points sit at 0), so every reduction order and tie-break returns j:
+// the sampling is the identity prefix, and so is the sampling of any prefix of the cloud to any
+// m' <= m.  Same fp32 distance (sqdist3) and the same 1e10 start value as the chain.  Scenes that
+// fail any test (ties, duplicates, skipped points, NaNs) keep run_flag = 1 and go through the
+// real chain, so the result is the reference's in every case.
+constexpr int kVerT = 256;
+
+__global__ void __launch_bounds__(kVerT)
+fps_prefix_v_kernel(int n, int m, const float *__restrict__ xyz_all, float *__restrict__ v_all,
+                    int *__restrict__ run_flags) {
+  extern __shared__ float spts[];      // the first m points, xyz interleaved
+  const int scene = blockIdx.y;
+  const float *xyz = xyz_all + (size_t)scene * n * 3;
+  for (int e = threadIdx.x; e < m * 3; e += kVerT) spts[e] = xyz[e];
+  __syncthreads();
+  const int j = blockIdx.x * kVerT + threadIdx.x;
+  if (j >= m) return;
+  const float x = spts[j * 3], y = spts[j * 3 + 1], z = spts[j * 3 + 2];
+  float v = 1e10f;
+  for (int i = 0; i < j; ++i) v = fminf(v, sqdist3(x, y, z, spts[i * 3], spts[i * 3 + 1], spts[i * 3 + 2]));
+  v_all[(size_t)scene * m + j] = v;
+  if (j >= 1 && !(v > 0.f)) run_flags[scene] = 1;
+}
+
+__global__ void __launch_bounds__(kVerT)
+fps_prefix_check_kernel(int n, int m, const float *__restrict__ xyz_all,
+                        const float *__restrict__ v_all, int *__restrict__ run_flags) {
+  extern __shared__ float spts[];      // [3m] points, then [m] V
+  float *sv = spts + 3 * m;
+  const int scene = blockIdx.y;
+  const float *xyz = xyz_all + (size_t)scene * n * 3;
+  for (int e = threadIdx.x; e < m * 3; e += kVerT) spts[e] = xyz[e];
+  for (int e = threadIdx.x; e < m; e += kVerT) sv[e] = v_all[(size_t)scene * m + e];
+  __syncthreads();
+  const int k = blockIdx.x * kVerT + threadIdx.x;
+  if (k < 1 || k >= n) return;
+  const float x = xyz[(size_t)k * 3], y = xyz[(size_t)k * 3 + 1], z = xyz[(size_t)k * 3 + 2];
+  const float mag = __fmaf_rn(z, z, __fmaf_rn(x, x, __fmul_rn(y, y)));
+  bool ok = !((double)mag <= 1e-3);                      // sampling_gpu.cu:100-101 skip set
+  const int jmax = min(k, m);
+  float r = 1e10f;
+  for (int j = 1; j < jmax; ++j) {
+    r = fminf(r, sqdist3(x, y, z, spts[(j - 1) * 3], spts[(j - 1) * 3 + 1], spts[(j - 1) * 3 + 2]));
+    ok = ok && (r < sv[j]);
+  }
+  if (!ok) run_flags[scene] = 1;
+}
+
+__global__ void __launch_bounds__(256)
+fps_identity_fill_kernel(int n, int m, const float *__restrict__ xyz_all, const int *__restrict__ run_flags,
+                         int *__restrict__ idx_all, float *__restrict__ new_xyz_all) {
+  const int scene = blockIdx.y;
+  if (run_flags[scene] != 0) return;
+  const int e = blockIdx.x * 256 + threadIdx.x;
+  if (e < m) idx_all[(size_t)scene * m + e] = e;
+  if (new_xyz_all && e < m * 3) new_xyz_all[(size_t)scene * m * 3 + e] = xyz_all[(size_t)scene * n * 3 + e];
+}
+
+// prefix lengths whose coordinates + V fit the check kernel's shared memory
+bool fps_prefix_check_supported(int n, int m) { return m >= 1 && m <= n && m <= 8192; }
+
+int fps_prefix_check_dispatch(int b, int n, int m, const float *xyz, float *v_scratch, int *run_flags,
+                              cudaStream_t stream) {
+  if (b > 65535) return set_error(BQA_ERR_UNSUPPORTED, "fps prefix check: batch too large");
+  BQA_CUDA(cudaMemsetAsync(run_flags, 0, sizeof(int) * (size_t)b, stream));
+  static bool attr_done = false;
+  if (!attr_done) {
+    BQA_CUDA(cudaFuncSetAttribute(fps_prefix_v_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 8192 * 12));
+    BQA_CUDA(cudaFuncSetAttribute(fps_prefix_check_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 8192 * 16));
+    attr_done = true;
+  }
+  fps_prefix_v_kernel<<<dim3((unsigned)ceil_div(m, kVerT), (unsigned)b), kVerT, (size_t)m * 12, stream>>>(
+      n, m, xyz, v_scratch, run_flags);
+  count_launch();
+  if (int rc = check_launch("fps_prefix_v_kernel")) return rc;
+  fps_prefix_check_kernel<<<dim3((unsigned)ceil_div(n, kVerT), (unsigned)b), kVerT, (size_t)m * 16, stream>>>(
+      n, m, xyz, v_scratch, run_flags);
+  count_launch();
+  return check_launch("fps_prefix_check_kernel");
+}
+
+int fps_identity_fill_dispatch(int b, int n, int m, const float *xyz, const int *run_flags, int *idxs,
+                               float *new_xyz, cudaStream_t stream) {
+  fps_identity_fill_kernel<<<dim3((unsigned)ceil_div(m * 3, 256), (unsigned)b), 256, 0, stream>>>(
+      n, m, xyz, run_flags, idxs, new_xyz);
+  count_launch();
+  return check_launch("fps_identity_fill_kernel");
 }
 
 }  // namespace bqa

@@ -52,6 +52,7 @@ class Pointnet2Backbone(nn.Module):
         import os
         self.sa1_slices = int(os.environ.get("BQA_SA1_SLICES", "1"))
         self.sa1_exclusive = os.environ.get("BQA_FPS_EXCLUSIVE", "1") != "0"
+        self.prefix_check = os.environ.get("BQA_FPS_PREFIX_CHECK", "1") != "0"
         self.fp1 = PointnetFPModule(mlp=[c + c, c, c])
         self.fp2 = PointnetFPModule(mlp=[c + c, c, seed_feat_dim])
 
@@ -68,9 +69,12 @@ class Pointnet2Backbone(nn.Module):
         return xyz, features
 
     def _sample_lower_levels(self, xyz1):
-        """Inference only.  The FPS stages depend on coordinates alone, so levels 2-4 (16 small
-        CTAs, ~0.6 ms of serial latency) run on a side stream underneath SA1's ball query + MLP
-        instead of in front of SA2/3/4.  Returns [(inds, new_xyz, event)] for SA2..SA4."""
+        """Inference only.  The FPS stages depend on coordinates alone, so levels 2-4 run on a
+        side stream underneath SA1's ball query + MLP instead of in front of SA2/3/4.  Their
+        input is a cloud already in sampling order, so one parallel check (fused.fps_prefix_check)
+        usually proves that all three samplings are identity prefixes and the serial chains
+        (~0.7 ms) are skipped; scenes it cannot prove go through the chain as before.
+        Returns [(inds, new_xyz, event)] for SA2..SA4."""
         main = torch.cuda.current_stream(xyz1.device)
         side = fused.side_stream(xyz1.device, "fps_levels")
         out = []
@@ -79,8 +83,15 @@ class Pointnet2Backbone(nn.Module):
         with torch.cuda.stream(side):
             side.wait_event(ready)
             cur = xyz1
+            covered = 0 < self.sa2.npoint <= min(xyz1.size(1), 8192) and self.prefix_check
+            flags = fused.fps_prefix_check(xyz1, self.sa2.npoint) if covered else None
             for sa in (self.sa2, self.sa3, self.sa4):
-                inds, new_xyz = pointnet2_utils.furthest_point_sample_with_xyz(cur, sa.npoint)
+                if flags is not None and sa.npoint <= min(self.sa2.npoint, cur.size(1)):
+                    # cur is a prefix of xyz1 for flagged scenes (previous level = identity prefix)
+                    inds, new_xyz = fused.furthest_point_sample_cond(cur, sa.npoint, flags)
+                else:
+                    flags = None
+                    inds, new_xyz = pointnet2_utils.furthest_point_sample_with_xyz(cur, sa.npoint)
                 done = torch.cuda.Event()
                 done.record(side)
                 for t in (inds, new_xyz):
@@ -89,7 +100,23 @@ class Pointnet2Backbone(nn.Module):
                 cur = new_xyz
         return out
 
+    def enable_cuda_graph(self, on=True, bind_inputs=False):
+        """Inference forwards of a fixed input shape replay a captured CUDA graph (graphs.py);
+        the returned tensors are then static buffers the next call overwrites."""
+        from . import graphs
+        if on and (getattr(self, "_graph_runner", None) is None
+                   or self._graph_runner.bind_inputs != bind_inputs):
+            self._graph_runner = graphs.GraphedForward(self, self._forward_impl, bind_inputs)
+        self._graphed = self._graph_runner if on else None
+        return self
+
     def forward(self, data_dict):
+        g = getattr(self, "_graphed", None)
+        if g is not None and g.applicable(data_dict):
+            return g(data_dict)
+        return self._forward_impl(data_dict)
+
+    def _forward_impl(self, data_dict):
         xyz, features = self._break_up_pc(data_dict["point_clouds"])
 
         overlap = (fused.enabled() and xyz.is_cuda and not self.training
@@ -104,18 +131,26 @@ class Pointnet2Backbone(nn.Module):
             if piped is not None:
                 xyz1, feats1, inds1, done1 = piped
             else:
+                # the ball query's cell grid only needs xyz: built on a side stream under FPS1
+                grid1 = (fused.prebuild_ball_query_grid(xyz, self.sa1.radius)
+                         if self.sa1._can_fuse(xyz, features) else None)
                 inds1, xyz1 = pointnet2_utils.furthest_point_sample_with_xyz(xyz, self.sa1.npoint)
                 done1 = None
             levels = self._sample_lower_levels(xyz1)
+            # grids of levels 2-4: each needs the coordinates one sampling level up
+            grids = [fused.prebuild_ball_query_grid(xyz1, self.sa2.radius),
+                     fused.prebuild_ball_query_grid(levels[0][1], self.sa3.radius, after=levels[0][2]),
+                     fused.prebuild_ball_query_grid(levels[1][1], self.sa4.radius, after=levels[1][2])]
             if piped is None:
-                xyz1, feats1, inds1 = self.sa1(xyz, features, inds1, new_xyz=xyz1)
+                xyz1, feats1, inds1 = self.sa1(xyz, features, inds1, new_xyz=xyz1, grid=grid1)
             else:
                 main.wait_event(done1)
             outs = [(xyz1, feats1, inds1)]
             xyz, features = xyz1, feats1
-            for sa, (inds, new_xyz, event) in zip((self.sa2, self.sa3, self.sa4), levels):
+            for sa, (inds, new_xyz, event), grid in zip((self.sa2, self.sa3, self.sa4), levels, grids):
                 main.wait_event(event)
-                xyz, features, inds = sa(xyz, features, inds, new_xyz=new_xyz)
+                xyz, features, inds = sa(xyz, features, inds, new_xyz=new_xyz,
+                                         grid=grid if sa._can_fuse(xyz, features) else None)
                 outs.append((xyz, features, inds))
         else:
             outs = []
@@ -292,8 +327,25 @@ class VoteNetDetector(nn.Module):
             num_proposal, sampling, seed_feat_dim=seed_feat_dim, proposal_size=proposal_size,
             radius=vote_radius, nsample=vote_nsample)
 
+    def enable_cuda_graph(self, on=True, bind_inputs=False):
+        """See Pointnet2Backbone.enable_cuda_graph; here the whole detector forward is one graph."""
+        from . import graphs
+        if on and (getattr(self, "_graph_runner", None) is None
+                   or self._graph_runner.bind_inputs != bind_inputs):
+            self._graph_runner = graphs.GraphedForward(self, self._forward_impl, bind_inputs)
+        self._graphed = self._graph_runner if on else None
+        return self
+
     def forward(self, data_dict):
-        data_dict = self.detection_backbone(data_dict)
+        g = getattr(self, "_graphed", None)
+        if g is not None and g.applicable(data_dict):
+            return g(data_dict)
+        return self._forward_impl(data_dict)
+
+    def _forward_impl(self, data_dict):
+        bb = self.detection_backbone
+        # (a backbone with its own graph must not replay it inside this module's capture)
+        data_dict = bb._forward_impl(data_dict) if torch.cuda.is_current_stream_capturing() else bb(data_dict)
         xyz, features = data_dict["fp2_xyz"], data_dict["fp2_features"]
         data_dict["seed_inds"] = data_dict["fp2_inds"]
         data_dict["seed_xyz"] = xyz

@@ -161,13 +161,54 @@ def point_major(features):
     return _ext.transpose_to_point_major(features.contiguous())
 
 
-def sa_forward(xyz, new_xyz, features, radius, nsample, normalize_xyz, packed):
-    """-> new_features (B, C3, npoint) fp32, with a point-major twin attached as ._bqa_pm."""
+GRID_MIN_POINTS = 256      # prebuilt grids: below this a scan is as fast as the search
+
+
+def prebuild_ball_query_grid(xyz, radius, after=None):
+    """Bin `xyz` (B,N,3) into the ball query's cell grid on a side stream -- it only needs the
+    coordinates, so it runs underneath the furthest point sampling that produces the centres.
+    `after`: event that marks xyz complete when another stream produced it (default: the
+    current stream's position).  Returns (grid, event) for sa_forward(..., grid=...), or None
+    for scenes too small to bother."""
+    N.check_tensor(xyz, "xyz", _f32)
+    b, n, _ = xyz.shape
+    if n < GRID_MIN_POINTS:
+        return None
+    dev = xyz.device
+    main = torch.cuda.current_stream(dev)
+    side = side_stream(dev, "bq_grid")
+    grid = torch.empty((N.lib().bqa_ball_query_grid_bytes(b, n),), dtype=torch.uint8, device=dev)
+    ready = after
+    if ready is None:
+        ready = torch.cuda.Event()
+        ready.record(main)
+    with torch.cuda.device(dev), torch.cuda.stream(side):
+        side.wait_event(ready)
+        N.call("bqa_ball_query_grid_build", b, n, ctypes.c_float(radius), N.ptr(xyz), N.ptr(grid),
+               N.stream_ptr(dev))
+        built = torch.cuda.Event()
+        built.record(side)
+    grid.record_stream(side)
+    xyz.record_stream(side)
+    return grid, built
+
+
+def sa_forward(xyz, new_xyz, features, radius, nsample, normalize_xyz, packed, grid=None):
+    """-> new_features (B, C3, npoint) fp32, with a point-major twin attached as ._bqa_pm.
+    `grid`: optional (buffer, event) from prebuild_ball_query_grid(xyz, ...)."""
     N.check_tensor(xyz, "xyz", _f32)
     N.check_tensor(new_xyz, "new_xyz", _f32)
     b, n, _ = xyz.shape
     npoint = new_xyz.size(1)
-    idx = _ext.ball_query(new_xyz, xyz, radius, nsample)
+    if grid is not None:
+        torch.cuda.current_stream(xyz.device).wait_event(grid[1])
+        idx = torch.empty((b, npoint, int(nsample)), dtype=torch.int32, device=xyz.device)
+        with torch.cuda.device(xyz.device):
+            N.call("bqa_ball_query_grid_search", b, n, npoint, 0, npoint, ctypes.c_float(radius),
+                   int(nsample), N.ptr(new_xyz), N.ptr(xyz), N.ptr(idx), N.ptr(grid[0]),
+                   N.stream_ptr(xyz.device))
+    else:
+        idx = _ext.ball_query(new_xyz, xyz, radius, nsample)
     if features is not None:
         pm = point_major(features)
         c, stride = pm.size(2), pm.stride(1)
@@ -186,13 +227,46 @@ def sa_forward(xyz, new_xyz, features, radius, nsample, normalize_xyz, packed):
     return out_cm
 
 
+def fps_prefix_check(xyz, npoint):
+    """run_flags (B,) int32 for a cloud that should already be in sampling order (the previous
+    level's centres): 0 = re-sampling any prefix of it to <= npoint points provably returns the
+    identity prefix, 1 = that scene needs the real chain (bqa_fps_prefix_check)."""
+    N.check_tensor(xyz, "xyz", _f32)
+    b, n, _ = xyz.shape
+    flags = torch.empty((b,), dtype=torch.int32, device=xyz.device)
+    scratch = torch.empty((b, int(npoint)), dtype=_f32, device=xyz.device)
+    with torch.cuda.device(xyz.device):
+        N.call("bqa_fps_prefix_check", b, n, int(npoint), N.ptr(xyz), N.ptr(scratch), N.ptr(flags),
+               N.stream_ptr(xyz.device))
+    return flags
+
+
+def furthest_point_sample_cond(xyz, npoint, run_flags):
+    """(inds, new_xyz) == furthest_point_sample_with_xyz(xyz, npoint); scenes whose run_flag is 0
+    get the (proven) identity prefix without running the serial chain."""
+    N.check_tensor(xyz, "xyz", _f32)
+    b, n, _ = xyz.shape
+    m = int(npoint)
+    inds = torch.empty((b, m), dtype=torch.int32, device=xyz.device)
+    new_xyz = torch.empty((b, m, 3), dtype=_f32, device=xyz.device)
+    with torch.cuda.device(xyz.device):
+        nbytes = N.lib().bqa_fps_scratch_bytes(b, n)
+        scratch = torch.empty((nbytes // 4,), dtype=_f32, device=xyz.device) if nbytes else None
+        N.call("bqa_furthest_point_sampling_cond", b, n, m, N.ptr(xyz), N.ptr(run_flags), N.ptr(inds),
+               N.ptr(new_xyz), N.ptr(scratch), N.stream_ptr(xyz.device))
+    return inds, new_xyz
+
+
 _side_streams = {}
 
 
 def side_stream(device, tag):
+    """High-priority side streams: their kernels are short dependencies of the main stream's next
+    layer (grid builds, the sampling-order check, lower-level sampling); without priority their
+    CTAs queue behind the persistent SA kernels that fill every SM."""
     key = (device, tag)
     if key not in _side_streams:
-        _side_streams[key] = torch.cuda.Stream(device)
+        _side_streams[key] = torch.cuda.Stream(device, priority=-1)
     return _side_streams[key]
 
 

@@ -161,9 +161,10 @@ class PointnetSAModuleVotes(nn.Module):
             slices, exclusive)
         return new_xyz, feats, inds, done
 
-    def forward(self, xyz, features=None, inds=None, new_xyz=None):
+    def forward(self, xyz, features=None, inds=None, new_xyz=None, grid=None):
         """`new_xyz` (optional, beyond the reference signature): the centres xyz[inds] when the
-        caller already has them (e.g. from the FPS kernel's epilogue), skipping the gather."""
+        caller already has them (e.g. from the FPS kernel's epilogue), skipping the gather.
+        `grid` (optional): fused.prebuild_ball_query_grid(xyz, radius), built while sampling."""
         if inds is not None:
             assert inds.shape[1] == self.npoint
         if self.npoint is None:
@@ -173,7 +174,7 @@ class PointnetSAModuleVotes(nn.Module):
 
         if self._can_fuse(xyz, features):
             new_features = fused.sa_forward(xyz, new_xyz, features, self.radius, self.nsample,
-                                            self.normalize_xyz, self._packed())
+                                            self.normalize_xyz, self._packed(), grid=grid)
             return new_xyz, new_features, inds
 
         grouped = self.grouper(xyz, new_xyz, features)

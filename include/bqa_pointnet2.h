@@ -54,6 +54,22 @@ BQA_API long long bqa_fps_scratch_bytes(int b, int n);
 BQA_API int bqa_furthest_point_sampling(int b, int n, int m, const float *xyz, int *idxs,
                                 float *new_xyz, float *scratch, void *stream);
 
+/* Sampling a cloud that is already in sampling order (SA2-4 sample the previous level's
+ * centres, models/backbone_module.py:52-86, where the reference itself notes the result "is just
+ * 0,1,...,1023", :111).  bqa_fps_prefix_check proves that in parallel, per scene:
+ *   run_flags[s] = 0  when furthest_point_sampling(xyz[s, :n'], m') is PROVABLY (0,1,...,m'-1) for
+ *                     every n' <= n and m' <= min(m, n') -- every step has a strict unique maximum,
+ *                     so no reduction order or tie-break can matter;
+ *   run_flags[s] = 1  otherwise (ties, duplicates, points in the skip set, non-finite values).
+ * v_scratch: b*m floats.  bqa_furthest_point_sampling_cond then writes the identity prefix
+ * (idxs[s] = 0..m-1, new_xyz[s] = xyz[s, :m]) for scenes flagged 0 and runs the real serial chain
+ * for the others, so its output always equals bqa_furthest_point_sampling's.  */
+BQA_API int bqa_fps_prefix_check(int b, int n, int m, const float *xyz, float *v_scratch,
+                                 int *run_flags, void *stream);
+BQA_API int bqa_furthest_point_sampling_cond(int b, int n, int m, const float *xyz,
+                                             const int *run_flags, int *idxs, float *new_xyz,
+                                             float *scratch, void *stream);
+
 /* Sliced sampling: produce samples j_begin .. j_end-1 only (1 <= j_begin <= j_end <= m; sample 0
  * is written by the slice with j_begin == 1).  Slices must be issued in order on one stream; the
  * running min-distances travel between them in `state` (b,n) f32.  Results are identical to one
@@ -78,9 +94,10 @@ BQA_API int bqa_gather_points_grad(int b, int c, int n, int m, const float *grad
  * First `nsample` indices k (ascending) with d2 < radius*radius, first hit back-fills
  * the row, empty ball -> zeros.
  * workspace: optional device scratch of bqa_ball_query_workspace_bytes(b,n,m,nsample) bytes
- * (0 for small scenes).  With it, large scenes are scanned in index-ordered segments by
- * several CTAs per query block (~2.5x faster at 40k points); with NULL a single CTA per
- * query block scans the whole scene.  The result is identical either way.  */
+ * (0 for small scenes).  With it, scenes of >= 4096 points are binned into a cell grid and
+ * each ball only visits the cells it touches, and mid-size scenes are scanned in index-ordered
+ * segments by several CTAs per query block; with NULL a single CTA per query block scans the
+ * whole scene.  The result is identical either way.  */
 BQA_API long long bqa_ball_query_workspace_bytes(int b, int n, int m, int nsample);
 BQA_API int bqa_ball_query(int b, int n, int m, float radius, int nsample, const float *new_xyz,
                    const float *xyz, int *idx, void *workspace, void *stream);
@@ -91,6 +108,20 @@ BQA_API int bqa_ball_query(int b, int n, int m, float radius, int nsample, const
 BQA_API int bqa_ball_query_slice(int b, int n, int m_total, int j_begin, int j_count, float radius,
                                  int nsample, const float *new_xyz, const float *xyz, int *idx,
                                  void *workspace, void *stream);
+
+/* Cell-grid form for large scenes (what bqa_ball_query runs internally for n >= 4096 when it is
+ * given a workspace), split in two so that a caller can bin the scene -- which only needs xyz
+ * -- on another stream while the sampling that produces new_xyz is still running:
+ *   grid  : device buffer of bqa_ball_query_grid_bytes(b, n) bytes
+ *   build : counting sort of each scene into cells of about `radius` (4 short launches)
+ *   search: one warp per centre of the slice [j_begin, j_begin + j_count); identical rows to
+ *           bqa_ball_query for ANY radius (the cell size only affects speed).  */
+BQA_API long long bqa_ball_query_grid_bytes(int b, int n);
+BQA_API int bqa_ball_query_grid_build(int b, int n, float radius, const float *xyz, void *grid,
+                                      void *stream);
+BQA_API int bqa_ball_query_grid_search(int b, int n, int m_total, int j_begin, int j_count,
+                                       float radius, int nsample, const float *new_xyz,
+                                       const float *xyz, int *idx, const void *grid, void *stream);
 
 /* ---- grouping -----------------------------------------------------------------
  * replaces: group_points / group_points_grad, src/group_points.cpp:12-62,

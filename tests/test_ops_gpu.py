@@ -105,6 +105,48 @@ def test_fps_vs_reference_extension(ref_ext):
         assert torch.equal(got, want), (b, n, m)
 
 
+def test_fps_prefix_check_and_conditional_sampling(oracle_ops):
+    """Re-sampling a cloud that is in sampling order: the parallel proof + conditional chain must
+    return exactly what the plain chain returns, for clean scenes (proved: identity prefix),
+    scenes with injected ties / duplicates / skip-set points (not provable: chain) and clouds
+    that are not in sampling order at all."""
+    from bridgeqa_b200 import fused
+    b = 6
+    xyz = dev(scenes(b, 20000, first=41))
+    _, xyz1 = ext.furthest_point_sampling(xyz, 2048, return_xyz=True)
+    xyz1 = xyz1.clone()
+    xyz1[1, 1500] = xyz1[1, 700]                  # duplicate of a prefix point -> exact tie at step 700
+    xyz1[2, 900] = torch.tensor([0.01, 0.01, 0.01], device="cuda")    # reference skip set
+    xyz1[3] = xyz1[3, torch.randperm(2048, device="cuda")]            # not in sampling order
+    xyz1[4, 1000:1008] = xyz1[4, 1000]            # a block of identical points
+    flags = fused.fps_prefix_check(xyz1, 1024)
+    assert flags.tolist() == [0, 1, 1, 1, 1, 0], flags.tolist()
+    cur = xyz1
+    for m in (1024, 512, 256):
+        want_i, want_x = ext.furthest_point_sampling(cur, m, return_xyz=True)
+        got_i, got_x = fused.furthest_point_sample_cond(cur, m, flags)
+        assert torch.equal(got_i, want_i) and torch.equal(got_x, want_x), m
+        np.testing.assert_array_equal(got_i.cpu().numpy(),
+                                      oracle_ops.furthest_point_sampling(cur.cpu().numpy(), m))
+        ident = torch.arange(m, device="cuda", dtype=torch.int32)
+        for s in (0, 5):
+            assert torch.equal(want_i[s], ident)          # what the proof claims
+        cur = got_x
+
+
+def test_fps_prefix_check_lattice_ties(oracle_ops):
+    """Lattice clouds tie constantly; put one in its own sampling order and check again."""
+    g = np.stack(np.meshgrid(np.arange(12), np.arange(12), np.arange(8), indexing="ij"), -1)
+    pts = (g.reshape(1, -1, 3).astype(np.float32) * np.float32(0.25) + np.float32(0.5))
+    order = oracle_ops.furthest_point_sampling(pts, pts.shape[1])[0].astype(np.int64)
+    from bridgeqa_b200 import fused
+    cloud = dev(pts[:, order])
+    flags = fused.fps_prefix_check(cloud, 512)
+    got_i, _ = fused.furthest_point_sample_cond(cloud, 512, flags)
+    np.testing.assert_array_equal(got_i.cpu().numpy(),
+                                  oracle_ops.furthest_point_sampling(pts[:, order], 512))
+
+
 # ----------------------------------------------------------------- ball query ---
 
 BQ_CASES = [
@@ -152,6 +194,81 @@ def test_ball_query_vs_reference_extension(ref_ext):
         want = ref_ext.ball_query(centres, xyz, r, ns)
         got = ext.ball_query(centres, xyz, r, ns)
         assert torch.equal(got, want), (b, n, m)
+
+
+def _ball_query_scan(centres, xyz, r, ns):
+    """The index-order scan kernel (no workspace => no grid, no segments)."""
+    import ctypes
+    from bridgeqa_b200 import _native as N
+    b, m, _ = centres.shape
+    idx = torch.empty((b, m, ns), dtype=torch.int32, device="cuda")
+    N.call("bqa_ball_query", b, xyz.size(1), m, ctypes.c_float(r), ns, N.ptr(centres), N.ptr(xyz),
+           N.ptr(idx), ctypes.c_void_p(0), N.stream_ptr(xyz.device))
+    return idx
+
+
+GRID_CASES = [
+    # (B, N, M, radius, nsample): the cell-grid path (n >= 8192) against the scan kernel
+    (2, 8192, 300, 0.2, 64), (3, 20000, 777, 0.35, 16), (2, 40000, 2048, 0.2, 64),
+    (1, 40000, 512, 1.5, 128), (1, 100000, 1000, 0.1, 32), (2, 9000, 64, 0.0, 8),
+    (1, 9000, 64, 50.0, 16), (2, 12000, 200, 0.2, 1),
+]
+
+
+@pytest.mark.parametrize("b,n,m,r,ns", GRID_CASES)
+def test_ball_query_grid_equals_scan(b, n, m, r, ns):
+    xyz = dev(scenes(b, n, first=23))
+    _, centres = ext.furthest_point_sampling(xyz, m, return_xyz=True)
+    centres = centres.clone()
+    centres[:, ::7] += 0.013            # off-sample centres too
+    assert torch.equal(ext.ball_query(centres, xyz, r, ns), _ball_query_scan(centres, xyz, r, ns))
+
+
+def test_ball_query_grid_adversarial(oracle_ops):
+    """Dense clutter (more hits than the per-warp list holds -> the in-kernel index-order
+    fallback), exact duplicates, points on cell borders, far outliers that stretch the bounding
+    box, non-finite coordinates, centres outside the box."""
+    rng = np.random.RandomState(5)
+    n = 10000
+    xyz = rng.uniform(-2, 2, size=(2, n, 3)).astype(np.float32)
+    xyz[0, 1000:3000] = np.float32([0.5, 0.5, 0.5]) + rng.normal(0, 0.01, size=(2000, 3)).astype(np.float32)
+    xyz[0, 4000:4700] = xyz[0, 4000]                           # 700 identical points
+    xyz[1, :, :] = np.round(xyz[1] / 0.25) * 0.25              # lattice: everything on cell borders
+    xyz[1, 17] = [1e6, -1e6, 3e5]                              # outliers
+    xyz[1, 18] = [-4e7, 0, 0]
+    xyz[0, 19] = [np.nan, 0.1, 0.1]
+    xyz[0, 20] = [np.inf, 0.1, 0.1]
+    xyz[0, 21] = [0.1, -np.inf, np.nan]
+    centres = np.concatenate([xyz[:, 990:1010], xyz[:, 3995:4005], xyz[:, 10:25],
+                              rng.uniform(-3, 3, size=(2, 40, 3)).astype(np.float32)], 1)
+    centres[0, -1] = [np.nan, 0, 0]
+    centres[1, -1] = [1e6, -1e6, 3e5]
+    centres = np.ascontiguousarray(centres)
+    for r, ns in [(0.25, 64), (0.05, 16), (0.6, 128), (0.25, 700)]:
+        want = oracle_ops.ball_query(centres, xyz, r, ns)
+        got = ext.ball_query(dev(centres), dev(xyz), r, ns).cpu().numpy()
+        np.testing.assert_array_equal(got, want, err_msg=str((r, ns)))
+        scan = _ball_query_scan(dev(centres), dev(xyz), r, ns).cpu().numpy()
+        np.testing.assert_array_equal(scan, want, err_msg="scan " + str((r, ns)))
+
+
+def test_ball_query_grid_split_api_any_build_radius():
+    """build (on any radius) + search over slices == the one-call form."""
+    import ctypes
+    from bridgeqa_b200 import _native as N
+    b, n, m, ns, r = 2, 30000, 600, 32, 0.3
+    xyz = dev(scenes(b, n, first=31))
+    _, centres = ext.furthest_point_sampling(xyz, m, return_xyz=True)
+    want = _ball_query_scan(centres, xyz, r, ns)
+    grid = torch.empty((N.lib().bqa_ball_query_grid_bytes(b, n),), dtype=torch.uint8, device="cuda")
+    for build_r in (0.3, 0.02, 5.0):
+        N.call("bqa_ball_query_grid_build", b, n, ctypes.c_float(build_r), N.ptr(xyz), N.ptr(grid),
+               N.stream_ptr(xyz.device))
+        idx = torch.full((b, m, ns), -1, dtype=torch.int32, device="cuda")
+        for lo, cnt in [(0, 100), (100, 499), (599, 1)]:
+            N.call("bqa_ball_query_grid_search", b, n, m, lo, cnt, ctypes.c_float(r), ns, N.ptr(centres),
+                   N.ptr(xyz), N.ptr(idx), N.ptr(grid), N.stream_ptr(xyz.device))
+        assert torch.equal(idx, want), build_r
 
 
 def test_ball_query_full_size_properties():
