@@ -43,6 +43,9 @@ int ref_opt_n_threads(int work_size) {
 int fps_dispatch(int b, int n, int m, int j_begin, int j_end, const float *xyz, int *idxs,
                  float *new_xyz, float *scratch, bool exclusive, const int *run_flags,
                  cudaStream_t stream);
+bool fps_sorted_supported(int n, int m);
+int fps_sorted_dispatch(int b, int n, int m, const float *xyz, const void *grid, int *idxs,
+                        float *new_xyz, cudaStream_t stream);
 bool fps_prefix_check_supported(int n, int m);
 int fps_prefix_check_dispatch(int b, int n, int m, const float *xyz, float *v_scratch, int *run_flags,
                               cudaStream_t stream);
@@ -109,6 +112,18 @@ int bqa_furthest_point_sampling(int b, int n, int m, const float *xyz, int *idxs
   BQA_REQUIRE(n > 0, "%s: n must be > 0 when m > 0", __func__);
   PTR(xyz); PTR(idxs);
   return fps_dispatch(b, n, m, 1, m, xyz, idxs, new_xyz, scratch, false, nullptr, (cudaStream_t)stream);
+}
+
+int bqa_fps_grid_supported(int n, int m) { return fps_sorted_supported(n, m) ? 1 : 0; }
+
+int bqa_furthest_point_sampling_grid(int b, int n, int m, const float *xyz, const void *grid, int *idxs,
+                                     float *new_xyz, void *stream) {
+  NONNEG(b); NONNEG(n); NONNEG(m);
+  if (b == 0 || m == 0) return BQA_OK;
+  BQA_REQUIRE(fps_sorted_supported(n, m), "%s: n=%d is outside what the sorted kernel takes "
+              "(see bqa_fps_grid_supported)", __func__, n);
+  PTR(xyz); PTR(grid); PTR(idxs);
+  return fps_sorted_dispatch(b, n, m, xyz, grid, idxs, new_xyz, (cudaStream_t)stream);
 }
 
 int bqa_fps_prefix_check(int b, int n, int m, const float *xyz, float *v_scratch, int *run_flags,

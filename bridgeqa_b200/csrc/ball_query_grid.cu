@@ -305,6 +305,10 @@ GridView carve(void *grid, int b, int n) {
 
 }  // namespace
 
+const float4 *ball_query_grid_sorted(const void *grid, int b, int n) {
+  return carve(const_cast<void *>(grid), b, n).sorted;
+}
+
 long long ball_query_grid_bytes(int b, int n) {
   return align256((long long)b * sizeof(GridHeader)) + 2 * align256(4ll * b * kCells) +
          align256(4ll * b * n) + align256(16ll * b * n);

@@ -100,7 +100,9 @@ namespace {
 // memory (574 cycles), handing results over through shared memory instead of redux/shfl, and
 // two scenes interleaved per 8-CTA cluster with a 17th communication warp (bit-exact, 28 %
 // fewer SM-cycles per scene, but 2024 cycles per pair-iteration vs 1517 for one scene on a
-// 6-CTA cluster, so the batch of 16 finishes later: 2.06 ms vs 1.58 ms).
+// 6-CTA cluster, so the batch of 16 finishes later: 2.06 ms vs 1.58 ms), and every warp pushing
+// its own candidate to every CTA (no CTA barrier, no warp-0 fold, each warp folds cs * 16
+// candidates; 192 small DSMEM stores per CTA and iteration instead of 12: 2.28 ms vs 1.58 ms).
 template <int P, int T>
 __global__ void __launch_bounds__(T, 1)
 fps_cluster_kernel(int n, int m, int j_begin, int j_end, int cs, uint32_t cs_magic, int bits,

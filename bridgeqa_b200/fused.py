@@ -164,20 +164,27 @@ def point_major(features):
 GRID_MIN_POINTS = 256      # prebuilt grids: below this a scan is as fast as the search
 
 
-def prebuild_ball_query_grid(xyz, radius, after=None):
-    """Bin `xyz` (B,N,3) into the ball query's cell grid on a side stream -- it only needs the
-    coordinates, so it runs underneath the furthest point sampling that produces the centres.
-    `after`: event that marks xyz complete when another stream produced it (default: the
-    current stream's position).  Returns (grid, event) for sa_forward(..., grid=...), or None
-    for scenes too small to bother."""
+def prebuild_ball_query_grid(xyz, radius, after=None, inline=False):
+    """Bin `xyz` (B,N,3) into the ball query's cell grid.  By default on a side stream -- the
+    build only needs the coordinates, so it runs underneath the sampling that produces the
+    centres; `after`: event that marks xyz complete when another stream produced it (default:
+    the current stream's position).  inline=True builds on the current stream instead (the
+    sampling itself is going to use the grid: furthest_point_sample_grid).
+    Returns (grid, event | None) for sa_forward(..., grid=...), or None for scenes too small
+    to bother."""
     N.check_tensor(xyz, "xyz", _f32)
     b, n, _ = xyz.shape
     if n < GRID_MIN_POINTS:
         return None
     dev = xyz.device
+    grid = torch.empty((N.lib().bqa_ball_query_grid_bytes(b, n),), dtype=torch.uint8, device=dev)
+    if inline:
+        with torch.cuda.device(dev):
+            N.call("bqa_ball_query_grid_build", b, n, ctypes.c_float(radius), N.ptr(xyz), N.ptr(grid),
+                   N.stream_ptr(dev))
+        return grid, None
     main = torch.cuda.current_stream(dev)
     side = side_stream(dev, "bq_grid")
-    grid = torch.empty((N.lib().bqa_ball_query_grid_bytes(b, n),), dtype=torch.uint8, device=dev)
     ready = after
     if ready is None:
         ready = torch.cuda.Event()
@@ -193,6 +200,27 @@ def prebuild_ball_query_grid(xyz, radius, after=None):
     return grid, built
 
 
+def fps_grid_supported(n, npoint):
+    return bool(N.lib().bqa_fps_grid_supported(int(n), int(npoint)))
+
+
+def furthest_point_sample_grid(xyz, npoint, grid):
+    """(inds, new_xyz) == furthest_point_sample_with_xyz(xyz, npoint), computed over the cell grid
+    `grid` = prebuild_ball_query_grid(xyz, ..., inline=True) with warp-level pruning
+    (fps_sorted.cu): bit-identical; 7-11 % less kernel time at 20k-100k points on B200."""
+    N.check_tensor(xyz, "xyz", _f32)
+    b, n, _ = xyz.shape
+    m = int(npoint)
+    if grid[1] is not None:
+        torch.cuda.current_stream(xyz.device).wait_event(grid[1])
+    inds = torch.empty((b, m), dtype=torch.int32, device=xyz.device)
+    new_xyz = torch.empty((b, m, 3), dtype=_f32, device=xyz.device)
+    with torch.cuda.device(xyz.device):
+        N.call("bqa_furthest_point_sampling_grid", b, n, m, N.ptr(xyz), N.ptr(grid[0]), N.ptr(inds),
+               N.ptr(new_xyz), N.stream_ptr(xyz.device))
+    return inds, new_xyz
+
+
 def sa_forward(xyz, new_xyz, features, radius, nsample, normalize_xyz, packed, grid=None):
     """-> new_features (B, C3, npoint) fp32, with a point-major twin attached as ._bqa_pm.
     `grid`: optional (buffer, event) from prebuild_ball_query_grid(xyz, ...)."""
@@ -201,7 +229,8 @@ def sa_forward(xyz, new_xyz, features, radius, nsample, normalize_xyz, packed, g
     b, n, _ = xyz.shape
     npoint = new_xyz.size(1)
     if grid is not None:
-        torch.cuda.current_stream(xyz.device).wait_event(grid[1])
+        if grid[1] is not None:
+            torch.cuda.current_stream(xyz.device).wait_event(grid[1])
         idx = torch.empty((b, npoint, int(nsample)), dtype=torch.int32, device=xyz.device)
         with torch.cuda.device(xyz.device):
             N.call("bqa_ball_query_grid_search", b, n, npoint, 0, npoint, ctypes.c_float(radius),

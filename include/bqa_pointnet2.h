@@ -54,6 +54,16 @@ BQA_API long long bqa_fps_scratch_bytes(int b, int n);
 BQA_API int bqa_furthest_point_sampling(int b, int n, int m, const float *xyz, int *idxs,
                                 float *new_xyz, float *scratch, void *stream);
 
+/* Sampling over the ball query's cell grid (bqa_ball_query_grid_build, below): the same result
+ * as bqa_furthest_point_sampling, bit for bit, but each warp holds a spatially compact run of the
+ * cell-sorted points and skips every iteration whose new sample provably cannot lower any of
+ * its min-distances (conservative bounding-box test), so only a few percent of the warps do the
+ * update in a typical iteration.  grid: the buffer built for this xyz (any radius).
+ * bqa_fps_grid_supported(n, m) != 0: 512 <= n <= 147456.  */
+BQA_API int bqa_fps_grid_supported(int n, int m);
+BQA_API int bqa_furthest_point_sampling_grid(int b, int n, int m, const float *xyz, const void *grid,
+                                             int *idxs, float *new_xyz, void *stream);
+
 /* Sampling a cloud that is already in sampling order (SA2-4 sample the previous level's
  * centres, models/backbone_module.py:52-86, where the reference itself notes the result "is just
  * 0,1,...,1023", :111).  bqa_fps_prefix_check proves that in parallel, per scene:

@@ -105,6 +105,55 @@ def test_fps_vs_reference_extension(ref_ext):
         assert torch.equal(got, want), (b, n, m)
 
 
+def _fps_grid(xyz, m, radius=0.2):
+    from bridgeqa_b200 import fused
+    grid = fused.prebuild_ball_query_grid(xyz, radius, inline=True)
+    return fused.furthest_point_sample_grid(xyz, m, grid)
+
+
+FPS_GRID_CASES = [
+    # (B, N, npoint, build radius) -- cluster sizes 1..16, ragged n, tiny and huge cells
+    (2, 512, 256, 0.4), (3, 1000, 333, 0.2), (2, 2048, 1024, 0.4), (2, 5000, 600, 0.2),
+    (2, 12345, 300, 0.05), (2, 20000, 512, 0.2), (4, 40000, 700, 0.2), (1, 40000, 2048, 3.0),
+    (1, 70000, 96, 0.2), (1, 100000, 64, 0.2), (1, 147456, 40, 0.2),
+]
+
+
+@pytest.mark.parametrize("b,n,m,r", FPS_GRID_CASES)
+def test_fps_grid_equals_plain_kernel(b, n, m, r):
+    xyz = dev(scenes(b, n, first=51))
+    want_i, want_x = ext.furthest_point_sampling(xyz, m, return_xyz=True)
+    got_i, got_x = _fps_grid(xyz, m, r)
+    assert torch.equal(got_i, want_i), (b, n, m)
+    assert torch.equal(got_x, want_x)
+
+
+def test_fps_grid_matches_oracle_on_ties_and_skips(oracle_ops):
+    """Lattice clouds (exact ties every iteration: the carried tie key must reproduce the
+    reference's pairwise tree), duplicates, the skip set, non-finite coordinates."""
+    rng = np.random.RandomState(7)
+    g = np.stack(np.meshgrid(np.arange(16), np.arange(16), np.arange(8), indexing="ij"), -1)
+    lattice = g.reshape(-1, 3).astype(np.float32) * np.float32(0.25) + np.float32(0.5)
+    pts = np.stack([lattice[rng.permutation(len(lattice))] for _ in range(2)])       # (2, 2048, 3)
+    pts[1, 100:140] = pts[1, 100]                     # duplicates
+    pts[1, 7] = [0.01, 0.02, 0.01]                    # |p|^2 <= 1e-3: never selectable
+    pts[1, 0] = [0.0, 0.0, 0.0]                       # ... but index 0 is always the first sample
+    want = oracle_ops.furthest_point_sampling(pts, 700)
+    got, _ = _fps_grid(dev(pts), 700, 0.25)
+    np.testing.assert_array_equal(got.cpu().numpy(), want)
+    # all points in the skip set -> every sample is index 0
+    tiny = (rng.uniform(-0.01, 0.01, size=(1, 600, 3))).astype(np.float32)
+    got, got_x = _fps_grid(dev(tiny), 50, 0.2)
+    assert (got == 0).all() and torch.equal(got_x[0, 5], dev(tiny)[0, 0])
+    # NaN / inf coordinates: same behaviour as the plain kernel
+    bad = scenes(1, 3000, first=3)
+    bad[0, 11] = [np.nan, 1.0, 1.0]
+    bad[0, 12] = [np.inf, 1.0, 1.0]
+    want_i = ext.furthest_point_sampling(dev(bad), 200)
+    got_i, _ = _fps_grid(dev(bad), 200, 0.2)
+    assert torch.equal(got_i, want_i)
+
+
 def test_fps_prefix_check_and_conditional_sampling(oracle_ops):
     """Re-sampling a cloud that is in sampling order: the parallel proof + conditional chain must
     return exactly what the plain chain returns, for clean scenes (proved: identity prefix),
