@@ -172,7 +172,7 @@ def run_reference_arm(args):
 def algorithmic_work(name, dims):
     """Algorithmic bytes (and flops) of one C-ABI call, from its integer arguments.
     Formulas: DESIGN.md 'Kernels' / SURVEY.md 8d."""
-    if name == "bqa_furthest_point_sampling":
+    if name in ("bqa_furthest_point_sampling", "bqa_furthest_point_sampling_grid", "bqa_furthest_point_sampling_cond"):
         b, n, m = dims[:3]
         return {"bytes": b * (12 * n + 4 * m + 12 * m), "bound": "hbm", "iters": m - 1, "units": b}
     if name == "bqa_ball_query":
@@ -181,6 +181,9 @@ def algorithmic_work(name, dims):
     if name == "bqa_ball_query_grid_search":
         b, n, m_total, j0, m, ns = dims[:6]
         return {"bytes": b * (12 * n + 12 * m + 4 * m * ns), "bound": "hbm", "pair_tests": b * n * m}
+    if name == "bqa_fps_prefix_check":
+        b, n, m = dims[:3]
+        return {"bytes": b * (12 * n + 4), "bound": "hbm"}
     if name == "bqa_ball_query_grid_build":
         b, n = dims[:2]
         return {"bytes": b * (12 * n + 16 * n), "bound": "hbm"}       # read xyz, write the cell-sorted float4 copy
@@ -495,8 +498,9 @@ def main():
         traffic = None
         try:   # dram__bytes_read + dram__bytes_write per launch from the committed ncu --set full capture
             prof = json.load(open(os.path.join(ROOT, "profiles", "r1_kernels_ncu.json")))
-            if top and top["kernel"] == "bqa_furthest_point_sampling" and top["dims"][:3] == [BATCH, NUM_POINTS, 2048]:
-                hit = [k for k in prof if k["kernel"].startswith("fps_cluster_kernel<14")]
+            names = {"bqa_furthest_point_sampling": "fps_cluster_kernel<14", "bqa_furthest_point_sampling_grid": "fps_sorted_kernel<14"}
+            if top and top["kernel"] in names and top["dims"][:3] == [BATCH, NUM_POINTS, 2048]:
+                hit = [k for k in prof if k["kernel"].startswith(names[top["kernel"]])]
                 if hit:
                     traffic = hit[0]["dram_read_bytes"] + hit[0]["dram_write_bytes"]
         except Exception:

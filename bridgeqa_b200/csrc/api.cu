@@ -43,6 +43,22 @@ int ref_opt_n_threads(int work_size) {
 int fps_dispatch(int b, int n, int m, int j_begin, int j_end, const float *xyz, int *idxs,
                  float *new_xyz, float *scratch, bool exclusive, const int *run_flags,
                  cudaStream_t stream);
+bool bn_relu_max_supported(int ns);
+int bn_stats_dispatch(int b, int c, long long l, const float *y, double *sums, float eps, float momentum,
+                      float *mean, float *invstd, float *running_mean, float *running_var,
+                      cudaStream_t stream);
+int bn_relu_apply_dispatch(int b, int c, long long l, const float *y, const float *mean, const float *invstd,
+                           const float *gamma, const float *beta, float *x, cudaStream_t stream);
+int bn_relu_max_dispatch(int b, int c, long long np, int ns, const float *y, const float *mean,
+                         const float *invstd, const float *gamma, const float *beta, float *out, int *argmax,
+                         cudaStream_t stream);
+int bn_relu_backward_dispatch(int b, int c, long long l, const float *dx, const float *y, const float *mean,
+                              const float *invstd, const float *gamma, const float *beta, double *sums,
+                              float *dy, float *dgamma, float *dbeta, cudaStream_t stream);
+int bn_relu_max_backward_dispatch(int b, int c, long long np, int ns, const float *dout, const int *argmax,
+                                  const float *y, const float *mean, const float *invstd, const float *gamma,
+                                  const float *beta, double *sums, float *dy, float *dgamma, float *dbeta,
+                                  cudaStream_t stream);
 bool fps_sorted_supported(int n, int m);
 int fps_sorted_dispatch(int b, int n, int m, const float *xyz, const void *grid, int *idxs,
                         float *new_xyz, cudaStream_t stream);
@@ -353,6 +369,71 @@ int bqa_fp_mlp_forward(int b, int n, int m, int c_known, int c_skip, const float
   return fp_forward_dispatch(b, n, m, c_known, c_skip, unknown, known, known_feat, known_stride,
                              skip_feat, skip_stride, c1, c2, w, b1, b2, out_cm, out_pm, precision,
                              (cudaStream_t)stream);
+}
+
+#define ALIGNED16(p) BQA_REQUIRE((reinterpret_cast<uintptr_t>(p) & 15) == 0, "%s: %s must be 16-byte aligned", __func__, #p)
+
+int bqa_bn_relu_max_supported(int nsample) { return bn_relu_max_supported(nsample) ? 1 : 0; }
+
+int bqa_bn_train_stats(int b, int c, long long l, const float *y, double *sums_scratch, float eps,
+                       float momentum, float *mean, float *invstd, float *running_mean,
+                       float *running_var, void *stream) {
+  NONNEG(b); NONNEG(c);
+  BQA_REQUIRE(l >= 0, "%s: l must be >= 0", __func__);
+  BQA_REQUIRE((long long)b * l > 0 || c == 0, "%s: batch statistics of an empty tensor", __func__);
+  if (c == 0) return BQA_OK;
+  PTR(y); PTR(sums_scratch); PTR(mean); PTR(invstd);
+  ALIGNED16(y);
+  return bn_stats_dispatch(b, c, l, y, sums_scratch, eps, momentum, mean, invstd, running_mean, running_var,
+                           (cudaStream_t)stream);
+}
+
+int bqa_bn_relu_forward(int b, int c, long long l, const float *y, const float *mean, const float *invstd,
+                        const float *gamma, const float *beta, float *x, void *stream) {
+  NONNEG(b); NONNEG(c);
+  if ((long long)b * c * l <= 0) return BQA_OK;
+  PTR(y); PTR(mean); PTR(invstd); PTR(gamma); PTR(beta); PTR(x);
+  ALIGNED16(y); ALIGNED16(x);
+  return bn_relu_apply_dispatch(b, c, l, y, mean, invstd, gamma, beta, x, (cudaStream_t)stream);
+}
+
+int bqa_bn_relu_max_forward(int b, int c, int npoint, int nsample, const float *y, const float *mean,
+                            const float *invstd, const float *gamma, const float *beta, float *out,
+                            int *argmax, void *stream) {
+  NONNEG(b); NONNEG(c); NONNEG(npoint);
+  BQA_REQUIRE(bn_relu_max_supported(nsample), "%s: nsample=%d must be a power of two in [4, 128]", __func__, nsample);
+  if ((long long)b * c * npoint == 0) return BQA_OK;
+  PTR(y); PTR(mean); PTR(invstd); PTR(gamma); PTR(beta); PTR(out); PTR(argmax);
+  ALIGNED16(y);
+  return bn_relu_max_dispatch(b, c, npoint, nsample, y, mean, invstd, gamma, beta, out, argmax,
+                              (cudaStream_t)stream);
+}
+
+int bqa_bn_relu_backward(int b, int c, long long l, const float *dx, const float *y, const float *mean,
+                         const float *invstd, const float *gamma, const float *beta, double *sums_scratch,
+                         float *dy, float *dgamma, float *dbeta, void *stream) {
+  NONNEG(b); NONNEG(c);
+  if (c == 0) return BQA_OK;
+  BQA_REQUIRE((long long)b * l > 0, "%s: empty tensor", __func__);
+  PTR(dx); PTR(y); PTR(mean); PTR(invstd); PTR(gamma); PTR(beta); PTR(sums_scratch); PTR(dy); PTR(dgamma); PTR(dbeta);
+  ALIGNED16(y); ALIGNED16(dx); ALIGNED16(dy);
+  return bn_relu_backward_dispatch(b, c, l, dx, y, mean, invstd, gamma, beta, sums_scratch, dy, dgamma, dbeta,
+                                   (cudaStream_t)stream);
+}
+
+int bqa_bn_relu_max_backward(int b, int c, int npoint, int nsample, const float *dout, const int *argmax,
+                             const float *y, const float *mean, const float *invstd, const float *gamma,
+                             const float *beta, double *sums_scratch, float *dy, float *dgamma, float *dbeta,
+                             void *stream) {
+  NONNEG(b); NONNEG(c); NONNEG(npoint);
+  BQA_REQUIRE(bn_relu_max_supported(nsample), "%s: nsample=%d must be a power of two in [4, 128]", __func__, nsample);
+  if (c == 0) return BQA_OK;
+  BQA_REQUIRE((long long)b * npoint > 0, "%s: empty tensor", __func__);
+  PTR(dout); PTR(argmax); PTR(y); PTR(mean); PTR(invstd); PTR(gamma); PTR(beta); PTR(sums_scratch); PTR(dy);
+  PTR(dgamma); PTR(dbeta);
+  ALIGNED16(y); ALIGNED16(dy);
+  return bn_relu_max_backward_dispatch(b, c, npoint, nsample, dout, argmax, y, mean, invstd, gamma, beta,
+                                       sums_scratch, dy, dgamma, dbeta, (cudaStream_t)stream);
 }
 
 }  // extern "C"

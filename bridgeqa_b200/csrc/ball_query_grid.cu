@@ -30,7 +30,7 @@
 namespace bqa {
 namespace {
 
-constexpr int kCells = 65536;        // cells per scene (cell size grows until the bbox fits)
+constexpr int kCells = 32768;        // cells per scene (cell size grows until the bbox fits)
 constexpr int kHitCap = 512;         // hits a warp can rank-sort in shared memory
 constexpr int kWarps = 8;            // queries per CTA
 constexpr int kGridMinPoints = 4096; // bqa_ball_query takes this path from here (given a workspace)
@@ -136,40 +136,62 @@ grid_count_kernel(int n, const float *__restrict__ xyz_all, GridView gv) {
   atomicAdd(&gv.start[(size_t)scene * kCells + c], 1);
 }
 
-// one CTA per scene: counts -> exclusive prefix sums (start) and a working copy (cursor)
+// one CTA per scene: counts -> exclusive prefix sums (start) and a working copy (cursor).
+// Each thread owns a run of cells (a multiple of 4, <= 64) that it keeps in registers as int4.
 __global__ void __launch_bounds__(1024)
 grid_scan_kernel(GridView gv) {
   __shared__ int warp_sum[32];
   const int scene = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const int cells = gv.header[scene].cells;
-  int *start = gv.start + (size_t)scene * kCells;
-  int *cursor = gv.cursor + (size_t)scene * kCells;
-  const int per = (cells + 1023) / 1024;
-  const int c0 = min(tid * per, cells), c1 = min(c0 + per, cells);
+  int4 *start4 = reinterpret_cast<int4 *>(gv.start + (size_t)scene * kCells);
+  int4 *cursor4 = reinterpret_cast<int4 *>(gv.cursor + (size_t)scene * kCells);
+  const int per4 = ((cells + 1023) / 1024 + 3) / 4;      // int4 groups per thread, 1..16
+  const int g0 = tid * per4;                             // first group of this thread
+  constexpr int kMaxGroups = kCells / 1024 / 4;
+  int4 v[kMaxGroups];
   int sum = 0;
-  for (int c = c0; c < c1; ++c) sum += start[c];
+#pragma unroll
+  for (int i = 0; i < kMaxGroups; ++i) {
+    v[i] = make_int4(0, 0, 0, 0);
+    if (i < per4) {
+      const int c = (g0 + i) * 4;
+      if (c < cells) {
+        v[i] = start4[g0 + i];
+        if (c + 1 >= cells) v[i].y = 0;                   // beyond the grid: never zeroed, ignore
+        if (c + 2 >= cells) v[i].z = 0;
+        if (c + 3 >= cells) v[i].w = 0;
+      }
+      sum += v[i].x + v[i].y + v[i].z + v[i].w;
+    }
+  }
   int incl = sum;
   for (int o = 1; o < 32; o <<= 1) {
-    const int v = __shfl_up_sync(0xffffffffu, incl, o);
-    if (lane >= o) incl += v;
+    const int t = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += t;
   }
   if (lane == 31) warp_sum[wid] = incl;
   __syncthreads();
   if (wid == 0) {
     int w = warp_sum[lane];
     for (int o = 1; o < 32; o <<= 1) {
-      const int v = __shfl_up_sync(0xffffffffu, w, o);
-      if (lane >= o) w += v;
+      const int t = __shfl_up_sync(0xffffffffu, w, o);
+      if (lane >= o) w += t;
     }
     warp_sum[lane] = w;
   }
   __syncthreads();
   int run = incl - sum + (wid ? warp_sum[wid - 1] : 0);
-  for (int c = c0; c < c1; ++c) {
-    const int cnt = start[c];
-    start[c] = run;
-    cursor[c] = run;
-    run += cnt;
+#pragma unroll
+  for (int i = 0; i < kMaxGroups; ++i) {
+    if (i < per4 && (g0 + i) * 4 < cells) {
+      int4 o;
+      o.x = run; run += v[i].x;
+      o.y = run; run += v[i].y;
+      o.z = run; run += v[i].z;
+      o.w = run; run += v[i].w;
+      start4[g0 + i] = o;
+      cursor4[g0 + i] = o;
+    }
   }
 }
 

@@ -67,7 +67,7 @@ class _PointnetSAModuleBase(nn.Module):
         self.mlps = None
 
     def _multi_scale(self, xyz, new_xyz, features):
-        outs = [_pool_max(mlp(grouper(xyz, new_xyz, features)))
+        outs = [mlp.forward_pooled(grouper(xyz, new_xyz, features))
                 for grouper, mlp in zip(self.groupers, self.mlps)]
         return torch.cat(outs, dim=1)
 
@@ -181,10 +181,14 @@ class PointnetSAModuleVotes(nn.Module):
         unique_cnt = grouped[2] if self.ret_unique_cnt else None
         grouped_features, grouped_xyz = grouped[0], grouped[1]
 
-        new_features = self.mlp_module(grouped_features)       # (B, mlp[-1], npoint, nsample)
         if self.pooling == 'max':
-            new_features = _pool_max(new_features)
-        elif self.pooling == 'avg':
+            # (B, mlp[-1], npoint, nsample) -> max over nsample, pointnet2_modules.py:259-262
+            new_features = self.mlp_module.forward_pooled(grouped_features)
+            if self.ret_unique_cnt:
+                return new_xyz, new_features, inds, unique_cnt
+            return new_xyz, new_features, inds
+        new_features = self.mlp_module(grouped_features)       # (B, mlp[-1], npoint, nsample)
+        if self.pooling == 'avg':
             new_features = F.avg_pool2d(new_features, kernel_size=[1, new_features.size(3)]).squeeze(-1)
         elif self.pooling == 'rbf':
             # RBF-weighted sum over the ball, normalised by nsample (pointnet2_modules.py:268-271)
@@ -215,7 +219,7 @@ class PointnetSAModuleMSGVotes(nn.Module):
             inds, new_xyz = _centres(xyz, self.npoint, inds)
         else:
             new_xyz = None
-        outs = [_pool_max(mlp(grouper(xyz, new_xyz, features)))
+        outs = [mlp.forward_pooled(grouper(xyz, new_xyz, features))
                 for grouper, mlp in zip(self.groupers, self.mlps)]
         return new_xyz, torch.cat(outs, dim=1), inds
 

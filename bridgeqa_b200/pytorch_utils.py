@@ -76,6 +76,49 @@ class _ConvBlock(nn.Sequential):
         if not preact:
             add_norm_act()
 
+    # -- training: conv -> [BatchNorm(batch stats) + ReLU] as one streaming autograd node ------
+    def _conv_bn_relu(self):
+        """(conv, norm) when this block is exactly conv -> BatchNorm -> ReLU, else None."""
+        mods = list(self.children())
+        if (len(mods) == 3 and isinstance(mods[0], self.conv_cls) and isinstance(mods[1], _NormWrapper)
+                and isinstance(mods[2], nn.ReLU)):
+            return mods[0], next(iter(mods[1].children()))
+        return None
+
+    def forward(self, x):
+        from . import train_fused
+        plan = self._conv_bn_relu() if (self.training and x.is_cuda) else None
+        if plan is not None:
+            conv, norm = plan
+            y = conv(x)
+            if train_fused.norm_supported(norm, y):
+                return train_fused.bn_relu(y, norm)
+            return mods_tail(self, y)
+        return super().forward(x)
+
+    def forward_pooled(self, x):
+        """max over the last axis of forward(x) -- for the last block of an SA layer
+        (pointnet2_modules.py:259-262); the (B,C,npoint,nsample) activation is not written when
+        the fused training kernel applies."""
+        from . import train_fused
+        plan = self._conv_bn_relu() if (self.training and x.is_cuda) else None
+        if plan is not None:
+            conv, norm = plan
+            y = conv(x)
+            if train_fused.norm_supported(norm, y) and train_fused.max_supported(y):
+                return train_fused.bn_relu_max(y, norm)
+            out = train_fused.bn_relu(y, norm) if train_fused.norm_supported(norm, y) else mods_tail(self, y)
+        else:
+            out = super().forward(x)
+        return torch.nn.functional.max_pool2d(out, kernel_size=[1, out.size(3)]).squeeze(-1)
+
+
+def mods_tail(block, y):
+    """the modules after the conv of a [conv, bn, act] block, applied to the conv's output"""
+    for m in list(block.children())[1:]:
+        y = m(y)
+    return y
+
 
 class Conv1d(_ConvBlock):
     conv_cls = nn.Conv1d
@@ -123,6 +166,14 @@ class SharedMLP(nn.Sequential):
                 name + "layer{}".format(i),
                 Conv2d(args[i], args[i + 1], bn=bn and not plain_input,
                        activation=None if plain_input else activation, preact=preact))
+
+    def forward_pooled(self, x):
+        """max_pool2d over nsample of forward(x), (B,C,npoint,nsample) -> (B,C,npoint), with the
+        pooling folded into the last block's BatchNorm + ReLU node when training on the GPU."""
+        blocks = list(self.children())
+        for blk in blocks[:-1]:
+            x = blk(x)
+        return blocks[-1].forward_pooled(x)
 
 
 class SharedMLPv2(nn.Sequential):

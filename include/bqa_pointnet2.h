@@ -221,6 +221,40 @@ BQA_API int bqa_fp_mlp_forward(int b, int n, int m, int c_known, int c_skip, con
                                const void *w, const float *b1, const float *b2, float *out_cm,
                                float *out_pm, int precision, void *stream);
 
+/* ---- train-mode BatchNorm + ReLU (+ max over nsample) --------------------------------------
+ * replaces, in model.train(), the nn.BatchNorm2d (training=True) + shared nn.ReLU that follow
+ * every 1x1 conv of a SharedMLP block (lib/pointnet2/pytorch_utils.py:11-36, 73-80) and, for the
+ * last block of an SA layer, the F.max_pool2d over nsample (pointnet2_modules.py:259-262), with
+ * their backward.  y, x, dx, dy: (b, c, l) contiguous fp32, 16-byte aligned (l = npoint*nsample).
+ *   bqa_bn_train_stats     : mean / invstd of the batch (biased variance, eps inside the sqrt) and
+ *                            the running-stat update (unbiased variance, momentum); either
+ *                            running pointer may be NULL.  sums_scratch: 2*c doubles.
+ *   bqa_bn_relu_forward    : x = relu(gamma * (y - mean) * invstd + beta)
+ *   bqa_bn_relu_max_forward: out (b,c,npoint) = max over nsample of the same, argmax (first
+ *                            occurrence, like max_pool2d) -- the activation is never written
+ *   bqa_bn_relu_backward   : dy, dgamma, dbeta from dx (gradient w.r.t. x) -- BatchNorm's
+ *                            training-mode backward with the ReLU mask recomputed from y
+ *   bqa_bn_relu_max_backward: same from dout (b,c,npoint) + argmax                              */
+BQA_API int bqa_bn_relu_max_supported(int nsample);
+BQA_API int bqa_bn_train_stats(int b, int c, long long l, const float *y, double *sums_scratch, float eps,
+                               float momentum, float *mean, float *invstd, float *running_mean,
+                               float *running_var, void *stream);
+BQA_API int bqa_bn_relu_forward(int b, int c, long long l, const float *y, const float *mean,
+                                const float *invstd, const float *gamma, const float *beta, float *x,
+                                void *stream);
+BQA_API int bqa_bn_relu_max_forward(int b, int c, int npoint, int nsample, const float *y,
+                                    const float *mean, const float *invstd, const float *gamma,
+                                    const float *beta, float *out, int *argmax, void *stream);
+BQA_API int bqa_bn_relu_backward(int b, int c, long long l, const float *dx, const float *y,
+                                 const float *mean, const float *invstd, const float *gamma,
+                                 const float *beta, double *sums_scratch, float *dy, float *dgamma,
+                                 float *dbeta, void *stream);
+BQA_API int bqa_bn_relu_max_backward(int b, int c, int npoint, int nsample, const float *dout,
+                                     const int *argmax, const float *y, const float *mean,
+                                     const float *invstd, const float *gamma, const float *beta,
+                                     double *sums_scratch, float *dy, float *dgamma, float *dbeta,
+                                     void *stream);
+
 /* ---- layout helper -------------------------------------------------------------
  * (b,c,n) channel-major -> (b,n,c) point-major, the layout the fused SA kernel gathers
  * from (one contiguous row per neighbour).  Replaces nothing in the reference; it is

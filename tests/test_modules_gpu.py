@@ -363,3 +363,74 @@ def test_cuda_graph_replay_equals_eager(which, c, _restore_fused):
         for k in keys:
             assert torch.equal(out[k], ref[k]), k
         assert not torch.equal(out[keys[0]], eager[0][keys[0]])
+
+
+@pytest.mark.parametrize("B,cin,spec,npoint,ns", [
+    (2, 6, [16, 16], 64, 16), (3, 10, [64, 64, 128], 128, 32), (2, 12, [128], 33, 64),
+    (2, 5, [8, 8], 10, 4), (2, 7, [16, 24], 20, 6),          # ns = 6: pooled falls back to max_pool2d
+])
+def test_train_bn_relu_max_matches_torch_modules(B, cin, spec, npoint, ns):
+    """csrc/bn_relu.cu behind SharedMLP in model.train(): outputs, running statistics and every
+    gradient equal those of the torch BatchNorm2d + ReLU + max_pool2d path."""
+    import copy
+    import torch.nn.functional as F
+    from bridgeqa_b200 import pytorch_utils as pt, train_fused
+    torch.manual_seed(3)
+    mlp_a = pt.SharedMLP([cin] + spec, bn=True).cuda().train()
+    for m in mlp_a.modules():
+        if isinstance(m, torch.nn.BatchNorm2d):
+            m.weight.data.uniform_(0.5, 1.5)
+            m.bias.data.uniform_(-0.5, 0.5)
+            m.momentum = 0.3
+    mlp_b = copy.deepcopy(mlp_a)
+    x = torch.randn(B, cin, npoint, ns, device="cuda")
+    x[..., ns // 2:] = x[..., :ns - ns // 2]                 # repeated neighbours: ties for the argmax
+    xa, xb = x.clone().requires_grad_(True), x.clone().requires_grad_(True)
+    w_full = torch.randn(B, spec[-1], npoint, ns, device="cuda")
+    w_pool = torch.randn(B, spec[-1], npoint, device="cuda")
+
+    for pooled in (False, True):
+        for net in (mlp_a, mlp_b):
+            net.zero_grad()
+        xa.grad = xb.grad = None
+        assert train_fused.enabled()
+        out_a = mlp_a.forward_pooled(xa) if pooled else mlp_a(xa)
+        train_fused.set_enabled(False)
+        try:
+            full_b = mlp_b(xb)
+            out_b = F.max_pool2d(full_b, kernel_size=[1, ns]).squeeze(-1) if pooled else full_b
+        finally:
+            train_fused.set_enabled(True)
+        w = w_pool if pooled else w_full
+        (out_a * w).sum().backward()
+        (out_b * w).sum().backward()
+        torch.testing.assert_close(out_a, out_b, rtol=1e-4, atol=1e-5)
+        torch.testing.assert_close(xa.grad, xb.grad, rtol=2e-3, atol=2e-5)
+        for (na, pa), (nb, pb) in zip(mlp_a.named_parameters(), mlp_b.named_parameters()):
+            torch.testing.assert_close(pa.grad, pb.grad, rtol=2e-3, atol=1e-4, msg=lambda m: na + ": " + m)
+        for (na, ba), (nb, bb) in zip(mlp_a.named_buffers(), mlp_b.named_buffers()):
+            torch.testing.assert_close(ba, bb, rtol=1e-5, atol=1e-6, msg=lambda m: na + ": " + m)
+
+
+def test_train_bn_relu_on_1d_rows_and_odd_lengths():
+    """FP-layer shape (B, C, n, 1) with n not a multiple of 4 (scalar path of the kernels)."""
+    import copy
+    from bridgeqa_b200 import pytorch_utils as pt, train_fused
+    torch.manual_seed(4)
+    a = pt.SharedMLP([9, 12, 12], bn=True).cuda().train()
+    b = copy.deepcopy(a)
+    x = torch.randn(3, 9, 77, 1, device="cuda")
+    xa, xb = x.clone().requires_grad_(True), x.clone().requires_grad_(True)
+    ya = a(xa)
+    train_fused.set_enabled(False)
+    try:
+        yb = b(xb)
+    finally:
+        train_fused.set_enabled(True)
+    w = torch.randn_like(ya)
+    (ya * w).sum().backward()
+    (yb * w).sum().backward()
+    torch.testing.assert_close(ya, yb, rtol=1e-4, atol=1e-5)
+    torch.testing.assert_close(xa.grad, xb.grad, rtol=2e-3, atol=2e-5)
+    for pa, pb in zip(a.parameters(), b.parameters()):
+        torch.testing.assert_close(pa.grad, pb.grad, rtol=2e-3, atol=1e-4)
