@@ -125,38 +125,48 @@ bn_relu_apply_kernel(int c, long long l, const float *__restrict__ y, const floa
   }
 }
 
-// one thread per 4 consecutive neighbours; ns / 4 adjacent lanes hold one (b, c, centre) group
+// One (b, c) row per blockIdx.y; a thread handles kMaxU float4s (4 consecutive neighbours each),
+// ns / 4 adjacent lanes hold one (b, c, centre) group.  row4 = npoint * ns / 4 float4s per row.
+constexpr int kMaxU = 4;
+
 __global__ void __launch_bounds__(kThreads)
-bn_relu_max_kernel(int c, long long np, int ns, long long total4, const float *__restrict__ y,
+bn_relu_max_kernel(int c, int row4, int lpg_shift, const float *__restrict__ y,
                    const float *__restrict__ mean, const float *__restrict__ invstd,
                    const float *__restrict__ gamma, const float *__restrict__ beta,
                    float *__restrict__ out, int *__restrict__ argmax) {
-  const long long e = (long long)blockIdx.x * kThreads + threadIdx.x;
-  const int lpg = ns >> 2;                         // lanes per group: power of two, <= 32
-  const bool live = e < total4;
-  const long long group = (live ? e : total4 - 1) / lpg;          // (b*c + ch) * np + j
-  const int ch = (int)((group / np) % c);
+  const int ch = blockIdx.y % c;
   const Affine f = affine_of(ch, mean, invstd, gamma, beta);
-  float best = -INFINITY;
-  int bi = 0;
-  if (live) {
-    const float4 v = __ldg(reinterpret_cast<const float4 *>(y) + e);
-    const int s0 = (int)(e % lpg) * 4;
-    const float z0 = fmaf(v.x, f.a, f.b), z1 = fmaf(v.y, f.a, f.b), z2 = fmaf(v.z, f.a, f.b),
-                z3 = fmaf(v.w, f.a, f.b);
-    best = z0; bi = s0;
+  const size_t row = blockIdx.y;
+  const float4 *r4 = reinterpret_cast<const float4 *>(y) + row * row4;
+  const int lpg = 1 << lpg_shift;
+  const int e0 = blockIdx.x * (kThreads * kMaxU) + threadIdx.x;
+  float4 v[kMaxU];
+#pragma unroll
+  for (int u = 0; u < kMaxU; ++u) {
+    const int e = e0 + u * kThreads;
+    v[u] = e < row4 ? __ldg(r4 + e) : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+#pragma unroll
+  for (int u = 0; u < kMaxU; ++u) {
+    const int e = e0 + u * kThreads;
+    const int s0 = (e & (lpg - 1)) * 4;
+    const float z0 = fmaf(v[u].x, f.a, f.b), z1 = fmaf(v[u].y, f.a, f.b), z2 = fmaf(v[u].z, f.a, f.b),
+                z3 = fmaf(v[u].w, f.a, f.b);
+    float best = z0;
+    int bi = s0;
     if (z1 > best) { best = z1; bi = s0 + 1; }
     if (z2 > best) { best = z2; bi = s0 + 2; }
     if (z3 > best) { best = z3; bi = s0 + 3; }
-  }
-  for (int o = 1; o < lpg; o <<= 1) {              // groups are lpg-aligned inside the warp
-    const float ov = __shfl_xor_sync(0xffffffffu, best, o);
-    const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-    if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
-  }
-  if (live && (e % lpg) == 0) {
-    out[group] = fmaxf(best, 0.f);
-    argmax[group] = bi;
+    for (int o = 1; o < lpg; o <<= 1) {            // groups are lpg-aligned inside the warp
+      const float ov = __shfl_xor_sync(0xffffffffu, best, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+      if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
+    }
+    if (e < row4 && (e & (lpg - 1)) == 0) {
+      const size_t g = row * (size_t)(row4 >> lpg_shift) + (size_t)(e >> lpg_shift);
+      out[g] = fmaxf(best, 0.f);
+      argmax[g] = bi;
+    }
   }
 }
 
@@ -244,29 +254,43 @@ bn_relu_max_bwd_stats_kernel(int c, long long np, int ns, const float *__restric
 }
 
 __global__ void __launch_bounds__(kThreads)
-bn_relu_max_bwd_apply_kernel(int c, long long np, int ns, long long total4, double count,
+bn_relu_max_bwd_apply_kernel(int c, int row4, int lpg_shift, double count,
                              const float *__restrict__ dout, const int *__restrict__ argmax,
                              const float *__restrict__ y, const float *__restrict__ mean,
                              const float *__restrict__ invstd, const float *__restrict__ gamma,
                              const float *__restrict__ beta, const double *__restrict__ sums,
                              float *__restrict__ dy) {
-  const long long e = (long long)blockIdx.x * kThreads + threadIdx.x;
-  if (e >= total4) return;
-  const int lpg = ns >> 2;
-  const long long group = e / lpg;
-  const int ch = (int)((group / np) % c);
+  const int ch = blockIdx.y % c;
   const Affine f = affine_of(ch, mean, invstd, gamma, beta);
   const float m1 = (float)(sums[ch] / count), m2 = (float)(sums[c + ch] / count);
-  const int s0 = (int)(e % lpg) * 4;
-  const int p = __ldg(argmax + group);
-  const float g = __ldg(dout + group);
-  const float4 v = __ldg(reinterpret_cast<const float4 *>(y) + e);
-  auto grad = [&](float yv, int s) {
-    const float dz = (s == p && fmaf(yv, f.a, f.b) > 0.f) ? g : 0.f;
-    return f.a * (dz - m1 - ((yv - f.mean) * f.invstd) * m2);
-  };
-  reinterpret_cast<float4 *>(dy)[e] =
-      make_float4(grad(v.x, s0), grad(v.y, s0 + 1), grad(v.z, s0 + 2), grad(v.w, s0 + 3));
+  const size_t row = blockIdx.y;
+  const float4 *r4 = reinterpret_cast<const float4 *>(y) + row * row4;
+  float4 *o4 = reinterpret_cast<float4 *>(dy) + row * row4;
+  const size_t g0 = row * (size_t)(row4 >> lpg_shift);
+  const int lpg = 1 << lpg_shift;
+  const int e0 = blockIdx.x * (kThreads * kMaxU) + threadIdx.x;
+  float4 v[kMaxU];
+  int p[kMaxU];
+  float g[kMaxU];
+#pragma unroll
+  for (int u = 0; u < kMaxU; ++u) {
+    const int e = e0 + u * kThreads;
+    const bool live = e < row4;
+    v[u] = live ? __ldg(r4 + e) : make_float4(0.f, 0.f, 0.f, 0.f);
+    p[u] = live ? __ldg(argmax + g0 + (e >> lpg_shift)) : -1;
+    g[u] = live ? __ldg(dout + g0 + (e >> lpg_shift)) : 0.f;
+  }
+#pragma unroll
+  for (int u = 0; u < kMaxU; ++u) {
+    const int e = e0 + u * kThreads;
+    if (e >= row4) continue;
+    const int s0 = (e & (lpg - 1)) * 4;
+    auto grad = [&](float yv, int s) {
+      const float dz = (s == p[u] && fmaf(yv, f.a, f.b) > 0.f) ? g[u] : 0.f;
+      return f.a * (dz - m1 - ((yv - f.mean) * f.invstd) * m2);
+    };
+    o4[e] = make_float4(grad(v[u].x, s0), grad(v[u].y, s0 + 1), grad(v[u].z, s0 + 2), grad(v[u].w, s0 + 3));
+  }
 }
 
 __global__ void bn_param_grad_kernel(int c, const double *__restrict__ sums, float *__restrict__ dgamma,
@@ -310,11 +334,15 @@ int bn_relu_apply_dispatch(int b, int c, long long l, const float *y, const floa
 int bn_relu_max_dispatch(int b, int c, long long np, int ns, const float *y, const float *mean,
                          const float *invstd, const float *gamma, const float *beta, float *out, int *argmax,
                          cudaStream_t stream) {
-  const long long total4 = (long long)b * c * np * (ns / 4);
-  const long long blocks = (total4 + kThreads - 1) / kThreads;
-  if (blocks > 0x7fffffffll) return set_error(BQA_ERR_UNSUPPORTED, "bn_relu_max: tensor too large");
-  bn_relu_max_kernel<<<(unsigned)blocks, kThreads, 0, stream>>>(c, np, ns, total4, y, mean, invstd, gamma,
-                                                               beta, out, argmax);
+  const long long row4 = np * (ns / 4);
+  if ((long long)b * c > 65535 || row4 > 0x7fffffffll)
+    return set_error(BQA_ERR_UNSUPPORTED, "bn_relu_max: b*c=%lld rows / %lld per row not supported",
+                     (long long)b * c, row4);
+  int shift = 0;
+  while ((4 << shift) < ns) ++shift;
+  dim3 grid((unsigned)((row4 + kThreads * kMaxU - 1) / (kThreads * kMaxU)), (unsigned)(b * c));
+  bn_relu_max_kernel<<<grid, kThreads, 0, stream>>>(c, (int)row4, shift, y, mean, invstd, gamma, beta, out,
+                                                   argmax);
   count_launch();
   return check_launch("bn_relu_max_kernel");
 }
@@ -348,11 +376,15 @@ int bn_relu_max_backward_dispatch(int b, int c, long long np, int ns, const floa
                                                           sums);
   count_launch();
   if (int rc = check_launch("bn_relu_max_bwd_stats_kernel")) return rc;
-  const long long total4 = (long long)b * c * np * (ns / 4);
-  const long long blocks = (total4 + kThreads - 1) / kThreads;
-  if (blocks > 0x7fffffffll) return set_error(BQA_ERR_UNSUPPORTED, "bn_relu_max: tensor too large");
-  bn_relu_max_bwd_apply_kernel<<<(unsigned)blocks, kThreads, 0, stream>>>(
-      c, np, ns, total4, (double)b * (double)np * (double)ns, dout, argmax, y, mean, invstd, gamma, beta, sums, dy);
+  const long long row4 = np * (ns / 4);
+  if ((long long)b * c > 65535 || row4 > 0x7fffffffll)
+    return set_error(BQA_ERR_UNSUPPORTED, "bn_relu_max: b*c=%lld rows / %lld per row not supported",
+                     (long long)b * c, row4);
+  int shift = 0;
+  while ((4 << shift) < ns) ++shift;
+  dim3 ag((unsigned)((row4 + kThreads * kMaxU - 1) / (kThreads * kMaxU)), (unsigned)(b * c));
+  bn_relu_max_bwd_apply_kernel<<<ag, kThreads, 0, stream>>>(
+      c, (int)row4, shift, (double)b * (double)np * (double)ns, dout, argmax, y, mean, invstd, gamma, beta, sums, dy);
   count_launch();
   if (int rc = check_launch("bn_relu_max_bwd_apply_kernel")) return rc;
   bn_param_grad_kernel<<<ceil_div(c, 128), 128, 0, stream>>>(c, sums, dgamma, dbeta);

@@ -164,9 +164,21 @@ class Pointnet2Backbone(nn.Module):
                                          grid=grid if sa._can_fuse(xyz, features) else None)
                 outs.append((xyz, features, inds))
         else:
+            # training / un-fused path: same layer sequence as the reference
+            # (models/backbone_module.py:97-121); on the GPU the re-sampling of sampled clouds at
+            # levels 2-4 still goes through the parallel identity-prefix proof
             outs = []
-            for sa in (self.sa1, self.sa2, self.sa3, self.sa4):
-                xyz, features, inds = sa(xyz, features)
+            flags = None
+            for k, sa in enumerate((self.sa1, self.sa2, self.sa3, self.sa4)):
+                inds = new_xyz = None
+                if k >= 1 and xyz.is_cuda and self.prefix_check and not xyz.requires_grad:
+                    if k == 1 and 0 < sa.npoint <= min(xyz.size(1), 8192):
+                        flags = fused.fps_prefix_check(xyz, sa.npoint)
+                    if flags is not None and sa.npoint <= min(self.sa2.npoint, xyz.size(1)):
+                        inds, new_xyz = fused.furthest_point_sample_cond(xyz, sa.npoint, flags)
+                    else:
+                        flags = None
+                xyz, features, inds = sa(xyz, features, inds, new_xyz=new_xyz)
                 outs.append((xyz, features, inds))
         data_dict["sa1_xyz"], data_dict["sa1_features"], data_dict["sa1_inds"] = outs[0]
         data_dict["sa2_xyz"], data_dict["sa2_features"], data_dict["sa2_inds"] = outs[1]
