@@ -82,6 +82,9 @@ int gather_rows_dispatch(int b, int c, int n, long long e_total, const float *po
 int scatter_add_rows_dispatch(int b, int c, int n, long long e_total, const float *grad_out,
                               const int *idx, float *grad_points, cudaStream_t stream);
 int transpose_cn_dispatch(int b, int c, int n, const float *in, float *out, cudaStream_t stream);
+int group_concat_pm_dispatch(int b, int n, int c, int feat_stride, long long e_total, int nsample, float radius,
+                             int normalize, const float *xyz, const float *new_xyz, const float *feat,
+                             const int *idx, float *out, cudaStream_t stream);
 int three_nn_dispatch(int b, int n, int m, const float *unknown, const float *known, float *dist2,
                       int *idx, cudaStream_t stream);
 int three_interpolate_dispatch(int b, int c, int m, int n, const float *points, const int *idx,
@@ -254,6 +257,20 @@ int bqa_group_points(int b, int c, int n, int npoints, int nsample, const float 
   if ((long long)b * c * e == 0) return BQA_OK;
   PTR(points); PTR(idx); PTR(out);
   return gather_rows_dispatch(b, c, n, e, points, idx, out, (cudaStream_t)stream);
+}
+
+int bqa_group_concat_point_major(int b, int n, int c, int feat_stride, int npoint, int nsample,
+                                 const float *xyz, const float *new_xyz, const float *feat_pm,
+                                 const int *idx, float radius, int normalize_xyz, float *out, void *stream) {
+  NONNEG(b); NONNEG(n); NONNEG(c); NONNEG(npoint); NONNEG(nsample);
+  const long long e = (long long)npoint * nsample;
+  if ((long long)b * e == 0) return BQA_OK;
+  PTR(xyz); PTR(new_xyz); PTR(idx); PTR(out);
+  if (c > 0) PTR(feat_pm);
+  BQA_REQUIRE(feat_stride >= c, "%s: feat_stride=%d < c=%d", __func__, feat_stride, c);
+  BQA_REQUIRE(!normalize_xyz || radius > 0.f, "%s: radius must be > 0", __func__);
+  return group_concat_pm_dispatch(b, n, c, feat_stride, e, nsample, radius, normalize_xyz, xyz, new_xyz,
+                                  feat_pm, idx, out, (cudaStream_t)stream);
 }
 
 int bqa_group_points_grad(int b, int c, int n, int npoints, int nsample, const float *grad_out,

@@ -77,6 +77,46 @@ int check_grid(long long e_total, int c, int b) {
   return BQA_OK;
 }
 
+// QueryAndGroup.forward in one pass (pointnet2_utils.py:347-359: two group_points launches,
+// subtract, divide, cat) for a POINT-MAJOR feature source -- the (B, N, 3+C) input cloud itself at
+// SA1.  out (B, 3+C, E) channel-major, E = npoint * nsample:
+//   out[b, 0:3, e] = (xyz[b, idx[e]] - new_xyz[b, e / nsample]) [/ radius]
+//   out[b, 3+k, e] = feat[b, idx[e], k]
+// A CTA owns 32 consecutive positions e: each warp reads whole feature rows (coalesced, C
+// contiguous floats) into a padded shared tile, then the tile is written back channel by channel
+// as 128-byte rows.  The channel-major gather it replaces reads 4 useful bytes per 32-byte sector.
+__global__ void __launch_bounds__(256)
+group_concat_pm_kernel(int n, int c, int feat_stride, long long e_total, int nsample, float radius,
+                       int normalize, const float *__restrict__ xyz, const float *__restrict__ new_xyz,
+                       const float *__restrict__ feat, const int *__restrict__ idx, float *__restrict__ out) {
+  extern __shared__ float tile[];                  // [c + 3][33]
+  __shared__ int s_idx[32];
+  const int scene = blockIdx.y;
+  const long long e0 = (long long)blockIdx.x * 32;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int npos = (int)min(32ll, e_total - e0);
+  if (threadIdx.x < 32) s_idx[threadIdx.x] = threadIdx.x < npos ? idx[(size_t)scene * e_total + e0 + threadIdx.x] : 0;
+  __syncthreads();
+  const long long npoint = e_total / nsample;
+  for (int pos = wid; pos < npos; pos += 8) {
+    const int k = s_idx[pos];
+    const float *row = feat + ((size_t)scene * n + k) * feat_stride;
+    for (int ch = lane; ch < c; ch += 32) tile[(3 + ch) * 33 + pos] = __ldg(row + ch);
+    if (lane < 3) {
+      const long long j = (e0 + pos) / nsample;
+      float v = xyz[((size_t)scene * n + k) * 3 + lane] - new_xyz[((size_t)scene * npoint + j) * 3 + lane];
+      // pointnet2_utils.py:351-352 `grouped_xyz /= radius`: on CUDA tensors torch evaluates a
+      // division by a Python scalar as a multiplication by fl(1.0f / fl(radius))
+      // (ATen BinaryDivTrueKernel.cu), which is what the reference therefore computes on the GPU
+      if (normalize) v = __fmul_rn(v, __fdiv_rn(1.0f, radius));
+      tile[lane * 33 + pos] = v;
+    }
+  }
+  __syncthreads();
+  for (int ch = wid; ch < c + 3; ch += 8)
+    if (lane < npos) out[((size_t)scene * (c + 3) + ch) * e_total + e0 + lane] = tile[ch * 33 + lane];
+}
+
 }  // namespace
 
 int gather_rows_dispatch(int b, int c, int n, long long e_total, const float *points,
@@ -109,4 +149,23 @@ int transpose_cn_dispatch(int b, int c, int n, const float *in, float *out, cuda
   return check_launch("transpose_cn_kernel");
 }
 
+}  // namespace bqa
+
+namespace bqa {
+int group_concat_pm_dispatch(int b, int n, int c, int feat_stride, long long e_total, int nsample, float radius,
+                             int normalize, const float *xyz, const float *new_xyz, const float *feat,
+                             const int *idx, float *out, cudaStream_t stream) {
+  const size_t smem = sizeof(float) * 33 * (size_t)(c + 3);
+  if (smem > 200 * 1024 || b > 65535) return set_error(BQA_ERR_UNSUPPORTED, "group_concat: c=%d too wide", c);
+  static size_t configured = 0;
+  if (smem > 48 * 1024 && smem > configured) {
+    BQA_CUDA(cudaFuncSetAttribute(group_concat_pm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = smem;
+  }
+  dim3 grid((unsigned)((e_total + 31) / 32), (unsigned)b);
+  group_concat_pm_kernel<<<grid, 256, smem, stream>>>(n, c, feat_stride, e_total, nsample, radius, normalize, xyz,
+                                                      new_xyz, feat, idx, out);
+  count_launch();
+  return check_launch("group_concat_pm_kernel");
+}
 }  // namespace bqa

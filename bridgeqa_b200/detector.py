@@ -63,7 +63,10 @@ class Pointnet2Backbone(nn.Module):
     @staticmethod
     def _break_up_pc(pc):
         xyz = pc[..., :3].contiguous()
-        features = pc[..., 3:].transpose(1, 2).contiguous() if pc.size(-1) > 3 else None
+        # (B,C,N) VIEW of the cloud (the reference materialises it, backbone_module.py:74-78): every
+        # consumer on the hot path gathers from the point-major twin below instead, so the
+        # transposed copy (338 MB at C=132) is only made by a consumer that really needs it
+        features = pc[..., 3:].transpose(1, 2) if pc.size(-1) > 3 else None
         if features is not None:
             # the input cloud already is the point-major layout the fused SA kernel gathers from;
             # when the channel count allows 16-byte loads (C % 4 == 0, e.g. the 132-d multiview

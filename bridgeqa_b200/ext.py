@@ -96,6 +96,25 @@ def group_points(points, idx):
     return out
 
 
+def group_concat_point_major(xyz, new_xyz, feat_pm, idx, radius, normalize_xyz):
+    """QueryAndGroup's grouping + centring + cat (pointnet2_utils.py:347-359) in one pass from a
+    point-major feature view feat_pm (B,N,C) with unit channel stride -> (B, 3+C, M, S)."""
+    N.check_tensor(xyz, "xyz", _f32)
+    N.check_tensor(new_xyz, "new_xyz", _f32)
+    N.check_tensor(idx, "idx", _i32)
+    if feat_pm.dtype != _f32 or not feat_pm.is_cuda or feat_pm.stride(2) != 1 or \
+            feat_pm.stride(0) != feat_pm.size(1) * feat_pm.stride(1):
+        raise RuntimeError("feat_pm must be a CUDA float (B,N,C) view with unit channel stride")
+    b, n, c = feat_pm.shape
+    _, npoints, nsample = idx.shape
+    out = torch.empty((b, 3 + c, npoints, nsample), dtype=_f32, device=xyz.device)
+    with _guard(xyz):
+        N.call("bqa_group_concat_point_major", b, n, c, feat_pm.stride(1), npoints, nsample, N.ptr(xyz),
+               N.ptr(new_xyz), N.ptr(feat_pm), N.ptr(idx), ctypes.c_float(radius),
+               1 if normalize_xyz else 0, N.ptr(out), N.stream_ptr(xyz.device))
+    return out
+
+
 def group_points_grad(grad_out, idx, n):
     """group_points.cpp:38-62.  grad_out (B,C,M,S), idx (B,M,S) -> (B,C,n)."""
     N.check_tensor(grad_out, "grad_out", _f32)

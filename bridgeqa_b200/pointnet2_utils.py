@@ -167,6 +167,26 @@ class QueryAndGroup(nn.Module):
         idx = ball_query(self.radius, self.nsample, xyz, new_xyz)
         unique_cnt = self._resample_uniformly(idx) if self.sample_uniformly else None
 
+        # one-pass grouping + centring + cat straight from a point-major twin of the features
+        # (the input cloud itself at SA1), when nothing here needs a gradient
+        pm = getattr(features, "_bqa_pm", None) if features is not None else None
+        if (pm is not None and self.use_xyz and xyz.is_cuda and pm.is_cuda and pm.dim() == 3
+                and pm.size(0) == features.size(0) and pm.size(1) == features.size(2)
+                and pm.size(2) == features.size(1) and pm.stride(2) == 1
+                and pm.stride(0) == pm.size(1) * pm.stride(1)
+                and not (torch.is_grad_enabled() and (xyz.requires_grad or new_xyz.requires_grad
+                                                      or features.requires_grad))):
+            new_features = _ext.group_concat_point_major(xyz, new_xyz, pm, idx, self.radius,
+                                                         self.normalize_xyz)
+            out = [new_features]
+            if self.ret_grouped_xyz:
+                out.append(new_features[:, :3])
+            if self.ret_unique_cnt:
+                out.append(unique_cnt)
+            return out[0] if len(out) == 1 else tuple(out)
+
+        if features is not None and not features.is_contiguous():
+            features = features.contiguous()
         grouped_xyz = grouping_operation(xyz.transpose(1, 2).contiguous(), idx)
         grouped_xyz = grouped_xyz - new_xyz.transpose(1, 2).unsqueeze(-1)
         if self.normalize_xyz:

@@ -139,6 +139,16 @@ BQA_API int bqa_ball_query_grid_search(int b, int n, int m_total, int j_begin, i
  * points (b,c,n), idx (b,npoints,nsample) -> out (b,c,npoints,nsample) */
 BQA_API int bqa_group_points(int b, int c, int n, int npoints, int nsample, const float *points,
                      const int *idx, float *out, void *stream);
+/* QueryAndGroup.forward after the ball query (pointnet2_utils.py:347-359: group xyz, subtract the
+ * centre, optionally divide by the radius, group the features, cat) in ONE pass, for a point-major
+ * feature source feat_pm (b, n, feat_stride) -- e.g. the (B,N,3+C) input cloud itself:
+ * out (b, 3+c, npoint, nsample) = [ (xyz[idx] - new_xyz) (* fl(1/radius), torch's CUDA evaluation
+ * of `/= radius`) ; feat_pm[idx, :c]^T ] -- bit-identical to the reference sequence on the GPU.
+ * Forward only (used when neither xyz nor the features need a gradient: SA1 of the backbone). */
+BQA_API int bqa_group_concat_point_major(int b, int n, int c, int feat_stride, int npoint, int nsample,
+                                         const float *xyz, const float *new_xyz, const float *feat_pm,
+                                         const int *idx, float radius, int normalize_xyz, float *out,
+                                         void *stream);
 BQA_API int bqa_group_points_grad(int b, int c, int n, int npoints, int nsample,
                           const float *grad_out, const int *idx, float *grad_points,
                           void *stream);

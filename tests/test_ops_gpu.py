@@ -360,6 +360,29 @@ def test_group_and_grad(oracle_ops, b, c, n, np_, ns):
     np.testing.assert_allclose(gg, oracle_ops.group_points_grad(go, idx, n), rtol=1e-4, atol=1e-4)
 
 
+@pytest.mark.parametrize("b,n,c,m,ns,r,norm", [(2, 3000, 7, 128, 16, 0.3, True), (2, 9000, 132, 200, 64, 0.2, True),
+                                                  (1, 700, 1, 33, 8, 0.5, False), (3, 2048, 128, 77, 32, 0.4, True)])
+def test_query_and_group_from_point_major_twin(b, n, c, m, ns, r, norm):
+    """One-pass grouping + centring + cat from the point-major cloud == the reference sequence
+    (two group_points, subtract, divide, cat; pointnet2_utils.py:347-359), bit for bit."""
+    pc = synthetic.make_batch(b, n, c, first_scene=61).cuda()
+    xyz = pc[..., :3].contiguous()
+    feats = pc[..., 3:].transpose(1, 2).contiguous()
+    _, new_xyz = ext.furthest_point_sampling(xyz, m, return_xyz=True)
+    grouper = pu.QueryAndGroup(r, ns, use_xyz=True, ret_grouped_xyz=True, normalize_xyz=norm)
+    want, want_xyz = grouper(xyz, new_xyz, feats)
+    view = pc[..., 3:].transpose(1, 2)               # what Pointnet2Backbone hands to SA1
+    view._bqa_pm = pc[..., 3:]
+    got, got_xyz = grouper(xyz, new_xyz, view)
+    assert torch.equal(got, want) and torch.equal(got_xyz, want_xyz)
+    # a gradient request must take the differentiable path
+    f2 = feats.clone().requires_grad_(True)
+    f2._bqa_pm = pc[..., 3:]
+    out, _ = grouper(xyz, new_xyz, f2)
+    out.sum().backward()
+    assert f2.grad is not None and torch.equal(out, want)
+
+
 def test_group_autograd_roundtrip():
     """grouping_operation backward == torch's own gather backward."""
     torch.manual_seed(0)
