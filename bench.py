@@ -181,6 +181,24 @@ def algorithmic_work(name, dims):
     if name == "bqa_ball_query_grid_search":
         b, n, m_total, j0, m, ns = dims[:6]
         return {"bytes": b * (12 * n + 12 * m + 4 * m * ns), "bound": "hbm", "pair_tests": b * n * m}
+    if name == "bqa_bn_train_stats":
+        b, c, l = dims[:3]
+        return {"bytes": 4 * b * c * l, "bound": "hbm"}
+    if name == "bqa_bn_relu_forward":
+        b, c, l = dims[:3]
+        return {"bytes": 8 * b * c * l, "bound": "hbm"}
+    if name == "bqa_bn_relu_max_forward":
+        b, c, npt, ns = dims[:4]
+        return {"bytes": 4 * b * c * npt * ns + 8 * b * c * npt, "bound": "hbm"}
+    if name == "bqa_bn_relu_backward":          # stats pass reads dx, y; apply pass reads dx, y, writes dy
+        b, c, l = dims[:3]
+        return {"bytes": 20 * b * c * l, "bound": "hbm"}
+    if name == "bqa_bn_relu_max_backward":      # dense pass: read y, write dy (dout / argmax are 1/nsample of that)
+        b, c, npt, ns = dims[:4]
+        return {"bytes": 8 * b * c * npt * ns + 12 * b * c * npt, "bound": "hbm"}
+    if name == "bqa_group_concat_point_major":
+        b, n, c, stride, npt, ns = dims[:6]
+        return {"bytes": b * npt * ns * (4 + 8 * (c + 3)), "bound": "hbm"}
     if name == "bqa_fps_prefix_check":
         b, n, m = dims[:3]
         return {"bytes": b * (12 * n + 4), "bound": "hbm"}
@@ -227,6 +245,9 @@ def run_train_mode(args, torch, dist, device, world, rank, real_stdout):
     pc = synthetic.make_batch(bsz, NUM_POINTS, feats, first_scene=rank * bsz).to(device)
     torch.backends.cudnn.allow_tf32 = True          # torch's (and the reference's) default
     torch.backends.cuda.matmul.allow_tf32 = True
+    if args.torch_bn:
+        from bridgeqa_b200 import train_fused
+        train_fused.set_enabled(False)
 
     def barrier():
         torch.cuda.synchronize()
@@ -248,17 +269,48 @@ def run_train_mode(args, torch, dist, device, world, rank, real_stdout):
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms = float(t[0])
+    launches = _native.launch_count() - l0
+    # per-kernel pass (one more step, CUDA events around every C-ABI call)
+    from bridgeqa_b200 import profiler
+    with profiler.KernelTimer() as kt:
+        k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        k0.record()
+        training.train_step(net, loss_fn, pc)
+        k1.record()
+        barrier()
+    kern = kt.summary()
+    kpass_ms = k0.elapsed_time(k1)
     if rank == 0:
+        peaks = measured_peaks()
+        groups = {}
+        for key, d in kern.items():
+            w = algorithmic_work(d["name"], d["dims"])
+            g = groups.setdefault(d["name"], {"kernel": d["name"], "calls_per_step": 0, "ms": 0.0, "bytes": 0})
+            g["calls_per_step"] += d["calls"]
+            g["ms"] += d["ms"]
+            g["bytes"] += w.get("bytes", 0) * d["calls"]
+        kernels = []
+        for g in groups.values():
+            row = {"kernel": g["kernel"], "calls_per_step": g["calls_per_step"], "ms": round(g["ms"], 4),
+                   "share": round(g["ms"] / kpass_ms, 4)}
+            if g["bytes"]:
+                ach = g["bytes"] / (g["ms"] / 1e3) / 1e9
+                row.update(bound="hbm", achieved=round(ach, 1), peak=peaks["hbm_gbs"], unit="GB/s",
+                           frac=round(ach / peaks["hbm_gbs"], 4))
+            kernels.append(row)
+        kernels.sort(key=lambda r: -r["ms"])
         nparam = sum(p.numel() for p in net.parameters())
         line = {"metric": "scenes/sec DET train step (fwd+bwd+grad all-reduce), 40k pts, C=132",
                 "value": bsz * world * args.steps / (ms / 1e3), "unit": UNIT, "n_gpus": world,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "tf32",
                 "data": "synthetic",
-                "config": {"workload": "VoteNetDetector fwd+bwd, train-mode BN, %d scenes/GPU, un-fused "
-                                       "differentiable operators + torch MLPs, one flat NCCL all-reduce of %d "
-                                       "fp32 gradients" % (bsz, nparam)},
-                "gpu_launches": _native.launch_count() - l0, "loss": float(loss)}
+                "config": {"workload": "VoteNetDetector fwd+bwd, train-mode BN, %d scenes/GPU: sm_100a operators "
+                                       "(sampling, grid ball query, grouping, BatchNorm+ReLU+max fwd/bwd) + cuDNN "
+                                       "TF32 1x1 convs, one flat NCCL all-reduce of %d fp32 gradients" % (bsz, nparam),
+                           "fused_bn_relu": bool(__import__("bridgeqa_b200.train_fused", fromlist=["x"]).enabled())},
+                "kernels": kernels, "kernel_pass_ms": round(kpass_ms, 3),
+                "gpu_launches": launches, "loss": float(loss)}
         sys.stdout.flush()
         os.dup2(real_stdout, 1)
         print(json.dumps(line), flush=True)
@@ -285,6 +337,8 @@ def main():
     ap.add_argument("--mode", default="forward", choices=["forward", "train"],
                     help="forward = BASELINE headline (configs[1]); train = DET train step, configs[3]")
     ap.add_argument("--train-batch", type=int, default=16, help="scenes per GPU in --mode train")
+    ap.add_argument("--torch-bn", action="store_true", help="--mode train: torch BatchNorm/ReLU/max_pool modules "
+                    "instead of the sm_100a streaming kernels (the reference's module structure)")
     ap.add_argument("--precision", default="fp16", choices=["fp16", "bf16"],
                     help="operand format of the fused tensor-core kernels (fp32 accumulate)")
     args = ap.parse_args()

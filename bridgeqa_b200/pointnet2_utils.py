@@ -131,6 +131,15 @@ class BallQuery(Function):
 ball_query = BallQuery.apply
 
 
+_state = {"group_concat": True}
+
+
+def set_group_concat(flag):
+    """Developer switch: False makes QueryAndGroup always run the reference's op sequence (two
+    group_points, subtract, divide, cat) instead of the one-pass kernel."""
+    _state["group_concat"] = bool(flag)
+
+
 class QueryAndGroup(nn.Module):
     """Ball query + grouping, un-fused (this is what training and the parity tests use;
     inference goes through the fused SA kernel and never builds this tensor).
@@ -170,7 +179,7 @@ class QueryAndGroup(nn.Module):
         # one-pass grouping + centring + cat straight from a point-major twin of the features
         # (the input cloud itself at SA1), when nothing here needs a gradient
         pm = getattr(features, "_bqa_pm", None) if features is not None else None
-        if (pm is not None and self.use_xyz and xyz.is_cuda and pm.is_cuda and pm.dim() == 3
+        if (pm is not None and _state["group_concat"] and self.use_xyz and xyz.is_cuda and pm.is_cuda and pm.dim() == 3
                 and pm.size(0) == features.size(0) and pm.size(1) == features.size(2)
                 and pm.size(2) == features.size(1) and pm.stride(2) == 1
                 and pm.stride(0) == pm.size(1) * pm.stride(1)

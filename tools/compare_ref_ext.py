@@ -103,11 +103,16 @@ def reference_pipeline_forward():
             return net({"point_clouds": pc})["fp2_features"]
 
     out = {"ours_fused_ms": round(timeit(fwd, warm=3, it=10), 3)}
+    net.enable_cuda_graph()
+    out["ours_fused_cuda_graph_ms"] = round(timeit(fwd, warm=3, it=10), 3)
+    net.enable_cuda_graph(False)
     bridgeqa_b200.set_fused(False)
     torch.backends.cudnn.allow_tf32 = True
     torch.backends.cuda.matmul.allow_tf32 = True
     out["ours_unfused_tf32_ms"] = round(timeit(fwd, warm=2, it=5), 3)
     if ref is not None:
+        pointnet2_utils.set_group_concat(False)      # the reference's op sequence, on its kernels
+        net.prefix_check = False
         saved = {}
         names = ["gather_points", "ball_query", "group_points", "three_nn", "three_interpolate"]
         for n in names:
@@ -127,9 +132,33 @@ def reference_pipeline_forward():
         finally:
             for n, f in saved.items():
                 setattr(our_ext, n, f)
+            pointnet2_utils.set_group_concat(True)
+    # configs[3]: DET training step (C=132), this repo vs the reference's kernels + torch modules
+    from bridgeqa_b200 import train_fused, training
+    pc132 = synthetic.make_batch(16, 40000, 132).cuda()
+    det = synthetic.fill_state_dict(detector.VoteNetDetector(132), seed=0).cuda()
+    loss_fn = training.ProjectionLoss().cuda()
+    out["ours_train_step_ms"] = round(timeit(lambda: training.train_step(det, loss_fn, pc132), warm=2, it=5), 3)
+    if ref is not None:
+        train_fused.set_enabled(False)
+        pointnet2_utils.set_group_concat(False)
+        det.detection_backbone.prefix_check = False
+        for n in names:
+            setattr(our_ext, n, getattr(ref, n))
+        our_ext.furthest_point_sampling = ref_fps
+        try:
+            out["reference_ext_train_step_ms"] = round(
+                timeit(lambda: training.train_step(det, loss_fn, pc132), warm=1, it=3), 3)
+        finally:
+            for n, f in saved.items():
+                setattr(our_ext, n, f)
+            train_fused.set_enabled(True)
+            pointnet2_utils.set_group_concat(True)
     bridgeqa_b200.set_fused(True)
-    out["speedup_vs_reference_ext_pipeline"] = (round(out["reference_ext_pipeline_ms"] / out["ours_fused_ms"], 1)
+    out["speedup_vs_reference_ext_pipeline"] = (round(out["reference_ext_pipeline_ms"] / out["ours_fused_cuda_graph_ms"], 1)
                                                 if "reference_ext_pipeline_ms" in out else None)
+    out["train_speedup_vs_reference_ext"] = (round(out["reference_ext_train_step_ms"] / out["ours_train_step_ms"], 1)
+                                             if "reference_ext_train_step_ms" in out else None)
     print(json.dumps({"backbone_forward_B16_N40000_C7": out}))
 
 
