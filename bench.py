@@ -519,7 +519,11 @@ def main():
 
     # max over ranks
     t = torch.tensor([elapsed_ms, e2e_ms], dtype=torch.float64, device=device)
+    by_rank = [elapsed_ms / args.steps]
     if world > 1:
+        every = [torch.zeros_like(t) for _ in range(world)]
+        dist.all_gather(every, t)
+        by_rank = [float(x[0]) / args.steps for x in every]       # device time of each rank's K steps
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     elapsed_ms, e2e_ms = float(t[0]), float(t[1])
 
@@ -590,6 +594,7 @@ def main():
                        "cuda_graph": not args.no_graph},
             "e2e": {"value": scenes / (e2e_ms / 1e3), "unit": UNIT, "ms_per_step": e2e_ms / args.steps,
                     "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes},
+            "ms_per_step_by_rank": [round(v, 4) for v in by_rank],
             "gpu_launches": launches,
             "host_issue_ms_per_step": round(host_issue_ms, 3),
             "kernel_pass": {"ms_per_step": round(kernel_pass_ms / args.steps, 4),

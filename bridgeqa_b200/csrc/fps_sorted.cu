@@ -43,7 +43,7 @@ constexpr unsigned kFull = 0xffffffffu;
 
 struct __align__(16) Cand {      // 32-byte slot, two 16-byte halves (st.async v4 + b32)
   uint32_t vb;                   // 0 = no selectable point, else float bits + 1
-  uint32_t nk;                   // (27-bit ~tie key) << 4 | poster id; larger wins
+  uint32_t nk;                   // (27-bit ~tie key) << 5 | slot or poster id; larger wins
   float x, y;
   float z;
   uint32_t pad[3];
@@ -52,12 +52,16 @@ struct __align__(16) Cand {      // 32-byte slot, two 16-byte halves (st.async v
 // 27-bit tie key for bs = 512: (bitrev9(k & 511) << 18) | (k >> 9); smaller wins.  k < 2^27.
 __device__ __forceinline__ uint32_t nkey_of(uint32_t k) {
   const uint32_t key = ((__brev(k & 511u) >> 23) << 18) | (k >> 9);
-  return (~key & 0x7ffffffu) << 4;
+  return (~key & 0x7ffffffu) << 5;
 }
 __device__ __forceinline__ uint32_t index_of(uint32_t nk) {
-  const uint32_t key = ~(nk >> 4) & 0x7ffffffu;
+  const uint32_t key = ~(nk >> 5) & 0x7ffffffu;
   return ((key & 0x3ffffu) << 9) | (__brev(key >> 18) >> 23);
 }
+
+#ifdef BQA_FPS_STATS
+__device__ unsigned long long g_active_warp_iters;
+#endif
 
 template <int P>
 __global__ void __launch_bounds__(kT, 1)
@@ -67,6 +71,7 @@ fps_sorted_kernel(int n, int m, int cs, const float4 *__restrict__ sorted_all,
   __shared__ Cand recv[2][kMaxCluster];
   __shared__ Cand part[kNW];
   __shared__ __align__(8) uint64_t bars[2];
+  extern __shared__ float4 pts[];        // [P][kT] copy of the coordinates: the winner's lookup by slot
 
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const uint32_t rank = cs > 1 ? cluster_ctarank() : 0u;
@@ -90,7 +95,7 @@ fps_sorted_kernel(int n, int m, int cs, const float4 *__restrict__ sorted_all,
     if (s < n) {
       const float4 v = sorted[s];
       x = v.x; y = v.y; z = v.z;
-      nk = nkey_of((uint32_t)__float_as_int(v.w));
+      nk = nkey_of((uint32_t)__float_as_int(v.w)) | (uint32_t)p;      // low 5 bits: my slot
       const float mag = __fmaf_rn(z, z, __fmaf_rn(x, x, __fmul_rn(y, y)));
       if (!((double)mag <= 1e-3)) t = 1e10f;             // sampling_gpu.cu:100-101, sampling.cpp:74-76
       lox = fminf(lox, x); hix = fmaxf(hix, x);          // fminf/fmaxf drop NaNs
@@ -98,6 +103,7 @@ fps_sorted_kernel(int n, int m, int cs, const float4 *__restrict__ sorted_all,
       loz = fminf(loz, z); hiz = fmaxf(hiz, z);
     }
     px[p] = x; py[p] = y; pz[p] = z; td[p] = t; nkey[p] = nk;
+    pts[p * kT + tid] = make_float4(x, y, z, 0.f);
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
@@ -139,7 +145,12 @@ fps_sorted_kernel(int n, int m, int cs, const float4 *__restrict__ sorted_all,
     const float ez = fmaxf(fmaxf(loz - z1, z1 - hiz), 0.f);
     const float lb = ex * ex + ey * ey + ez * ez;
     if (!(lb * 0.99999f >= wmax)) {
+#ifdef BQA_FPS_STATS
+      if (lane == 0) atomicAdd(&g_active_warp_iters, 1ull);
+#endif
       // ---- 1. update, warp max of the values ----------------------------------------------
+      // (a tree-shaped max and a key pass predicated on `best == wf` were both measured slower:
+      //  1.32 vs 1.26 ms -- the serial FMNMX chain hides under the distance arithmetic)
       float best = -INFINITY;
 #pragma unroll
       for (int p = 0; p < P; ++p) {
@@ -159,12 +170,9 @@ fps_sorted_kernel(int n, int m, int cs, const float4 *__restrict__ sorted_all,
         for (int p = 0; p < P; ++p) cand = max(cand, td[p] == wf ? nkey[p] : 0u);
         const uint32_t wnk = __reduce_max_sync(kFull, cand);
         if (cand == wnk) {                                 // exactly one lane (keys are distinct, non-zero)
-          float cx = 0.f, cy = 0.f, cz = 0.f;
-#pragma unroll
-          for (int p = 0; p < P; ++p)
-            if (nkey[p] == wnk) { cx = px[p]; cy = py[p]; cz = pz[p]; }
+          const float4 w = pts[(wnk & 31u) * kT + tid];    // own slot: no barrier needed
           Cand c;
-          c.vb = wvb; c.nk = wnk | (uint32_t)wid; c.x = cx; c.y = cy; c.z = cz;
+          c.vb = wvb; c.nk = (wnk & ~31u) | (uint32_t)wid; c.x = w.x; c.y = w.y; c.z = w.z;
           c.pad[0] = c.pad[1] = c.pad[2] = 0u;
           part[wid] = c;
         }
@@ -194,7 +202,7 @@ fps_sorted_kernel(int n, int m, int cs, const float4 *__restrict__ sorted_all,
         const uint32_t slot = smem_u32(&recv[jj & 1][rank]);
         if (lane == 0) mbar_arrive_expect_tx(bar, 20u * cs);
         if (lane < cs) {
-          st_async_v4(mapa_shared(slot, lane), mv, (mk & ~15u) | rank, __float_as_uint(wx), __float_as_uint(wy),
+          st_async_v4(mapa_shared(slot, lane), mv, (mk & ~31u) | rank, __float_as_uint(wx), __float_as_uint(wy),
                       mapa_shared(bar, lane));
         } else if (lane < 2 * cs) {
           st_async_b32(mapa_shared(slot + 16u, lane - cs), __float_as_uint(wz), mapa_shared(bar, lane - cs));
@@ -227,7 +235,9 @@ int launch_sorted(int b, int n, int m, int cs, const float4 *sorted, const float
   cudaLaunchAttribute attr[1];
   cfg.gridDim = dim3((unsigned)(b * cs));
   cfg.blockDim = dim3(kT);
-  cfg.dynamicSmemBytes = 0;
+  cfg.dynamicSmemBytes = sizeof(float4) * P * kT;
+  BQA_CUDA(cudaFuncSetAttribute(fps_sorted_kernel<P>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                (int)cfg.dynamicSmemBytes));
   cfg.stream = stream;
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = (unsigned)cs;
@@ -235,7 +245,17 @@ int launch_sorted(int b, int n, int m, int cs, const float4 *sorted, const float
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
+#ifdef BQA_FPS_STATS
+  unsigned long long zero = 0;
+  cudaMemcpyToSymbol(g_active_warp_iters, &zero, sizeof(zero));
+#endif
   BQA_CUDA(cudaLaunchKernelEx(&cfg, fps_sorted_kernel<P>, n, m, cs, sorted, xyz, idxs, new_xyz));
+#ifdef BQA_FPS_STATS
+  unsigned long long act = 0;
+  cudaMemcpyFromSymbol(&act, g_active_warp_iters, sizeof(act));
+  fprintf(stderr, "[bqa fps sorted] b=%d n=%d m=%d cs=%d P=%d: %.2f%% of warp-iterations active (%.1f warps per scene-iteration of %d)\n",
+          b, n, m, cs, P, 100.0 * act / ((double)b * cs * kNW * (m - 1)), (double)act / ((double)b * (m - 1)), cs * kNW);
+#endif
   count_launch();
   return check_launch("fps_sorted_kernel");
 }
