@@ -29,6 +29,8 @@
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
 
+#include <cstdio>
+
 #include "common.cuh"
 #include "tcgen05.cuh"
 
@@ -55,6 +57,7 @@ struct SaParams {
   int b, n, npoint, nsample, c;     // c = feature channels (K1 = c + 3); npoint = centres in this call
   int npoint_total, j_offset;       // the call covers centres [j_offset, j_offset + npoint) of npoint_total
   int k1pad;                        // K1 rounded up to a multiple of 16
+  int tail_sep;                     // the last 16 channels of K1 have their own A buffer (see kernel)
   int feat_stride;                  // floats between consecutive points of feat_pm (>= c)
   int feat_vec4;                    // rows are 16-byte aligned: float4 loads allowed
   const float *xyz, *new_xyz, *feat_pm;
@@ -73,13 +76,19 @@ struct SaParams {
 template <int CN>
 __device__ __forceinline__ void epilogue_rows(uint32_t tmem_d, int warp, int row, const float *s_bias,
                                               uint4 *x_buf, int fp16) {
+  static_assert(CN % 64 == 0, "two 32-column TMEM loads per step");
 #pragma unroll
-  for (int c0 = 0; c0 < CN; c0 += 32) {
-    uint32_t v[32];
-    umma::ld_32x32b_x32(tmem_d + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0, v);
+  for (int c0 = 0; c0 < CN; c0 += 64) {
+    // two tcgen05.ld in flight, one wait: the load latency is paid once per 64 columns
+    uint32_t va[32], vb[32];
+    umma::ld_32x32b_x32(tmem_d + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0, va);
+    umma::ld_32x32b_x32(tmem_d + ((uint32_t)(warp * 32) << 16) + (uint32_t)(c0 + 32), vb);
     umma::wait_ld();
+    uint32_t v[64];
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
+    for (int e = 0; e < 32; ++e) { v[e] = va[e]; v[32 + e] = vb[e]; }
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
       uint32_t p[4];
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
@@ -92,6 +101,15 @@ __device__ __forceinline__ void epilogue_rows(uint32_t tmem_d, int warp, int row
     }
   }
 }
+
+#ifdef BQA_SA_TRACE
+__device__ unsigned long long g_sa_trace[16];
+#define SA_TRACE_BEGIN const bool tr = blockIdx.x == 0 && threadIdx.x == 0; long long tc = clock64();
+#define SA_TRACE(i) if (tr) { const long long now = clock64(); g_sa_trace[i] += (unsigned long long)(now - tc); tc = now; }
+#else
+#define SA_TRACE_BEGIN
+#define SA_TRACE(i)
+#endif
 
 // named barrier over the 128 threads of one tile pipeline (id 1 or 2; 0 is __syncthreads)
 __device__ __forceinline__ void group_sync(int group) {
@@ -113,8 +131,10 @@ sa_mlp_max_kernel(const SaParams P) {
   static_assert((C1 + C2 > C3 ? C1 + C2 : C3) <= 256, "TMEM budget");
 
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  uint4 *ax_all = reinterpret_cast<uint4 *>(smem_raw);                // 2 x (A1 chunk / X1 / X2)
-  uint4 *w1s = ax_all + G * kAXVecs;                                  // [k1pad/8][C1]
+  constexpr int kTailVecs = 2 * kRows;                                // 16 channels x 128 rows
+  uint4 *ax_all = reinterpret_cast<uint4 *>(smem_raw);                // G x (A1 chunk / X1 / X2)
+  uint4 *tail_all = ax_all + G * kAXVecs;                             // G x last 16 channels of A1
+  uint4 *w1s = tail_all + (P.tail_sep ? G * kTailVecs : 0);           // [k1pad/8][C1]
   uint4 *w2s = w1s + (P.k1pad / 8) * C1;                              // [C1/8][C2]
   uint4 *w3s = w2s + (C1 / 8) * C2;                                   // [C2/8][C3]
   float *s_b1 = reinterpret_cast<float *>(w3s + (C2 / 8) * C3);
@@ -127,6 +147,7 @@ sa_mlp_max_kernel(const SaParams P) {
   const int tid = threadIdx.x & 127;        // row of the pipeline's tile
   const int warp = tid >> 5;                // TMEM lane quarter (warp_id % 4 of the real warp)
   uint4 *ax = ax_all + group * kAXVecs;
+  uint4 *ax_tail = tail_all + group * kTailVecs;
 
   // ---- one-time setup: weights + biases -> smem, mbarriers, TMEM ----------------------
   for (int i = threadIdx.x; i < (P.k1pad / 8) * C1; i += G * kRows) w1s[i] = P.w1p[i];
@@ -150,6 +171,7 @@ sa_mlp_max_kernel(const SaParams P) {
   const uint32_t tmem_d1 = tmem, tmem_d2 = tmem + C1, tmem_d3 = tmem;
   const uint32_t bar = smem_u32(&s_bar[group]);
 
+  const uint32_t ax_tail_addr = smem_u32(ax_tail);
   const uint32_t ax_addr = smem_u32(ax), w1_addr = smem_u32(w1s), w2_addr = smem_u32(w2s),
                  w3_addr = smem_u32(w3s);
   const uint32_t kIdesc1 = umma::instr_desc_16b_f32(128, C1, !P.fp16);
@@ -161,30 +183,83 @@ sa_mlp_max_kernel(const SaParams P) {
   const int centres_per_tile = kRows / ns;
   const int tiles_per_scene = P.npoint / centres_per_tile;
 
-  for (int tile = blockIdx.x * G + group; tile < P.num_tiles; tile += gridDim.x * G) {
+  // Per-row inputs of a tile: neighbour index i, its coordinates pp, the centre qq.  They are two
+  // dependent global loads (~2.7k cycles per tile when taken at the top of the tile), so the next
+  // tile's are fetched while this tile computes: i and qq at the top, pp (needs i) after layer 1.
+  auto row_of = [&](int tile, int &scene, int &j) {
+    scene = tile / tiles_per_scene;
+    j = P.j_offset + (tile % tiles_per_scene) * centres_per_tile + tid / ns;
+  };
+  const int tile_step = gridDim.x * G;
+  int tile = blockIdx.x * G + group;
+  int nx_i = 0;
+  float nx_pp[3] = {0.f, 0.f, 0.f}, nx_qq[3] = {0.f, 0.f, 0.f};
+  if (tile < P.num_tiles) {
+    int scene, j;
+    row_of(tile, scene, j);
+    nx_i = P.idx[((size_t)scene * P.npoint_total + j) * ns + (tid % ns)];
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+      nx_pp[d] = P.xyz[((size_t)scene * P.n + nx_i) * 3 + d];
+      nx_qq[d] = P.new_xyz[((size_t)scene * P.npoint_total + j) * 3 + d];
+    }
+  }
+  SA_TRACE_BEGIN
+  for (; tile < P.num_tiles; tile += tile_step) {
+    SA_TRACE(9)
     const int scene = tile / tiles_per_scene;
     const int centre0 = (tile % tiles_per_scene) * centres_per_tile;
-    // this thread's row: centre j, neighbour index i
-    const int j = P.j_offset + centre0 + tid / ns;           // centre index in the full layout
-    const int i = P.idx[((size_t)scene * P.npoint_total + j) * ns + (tid % ns)];
+    const int i = nx_i;
     const float *frow = P.feat_pm ? P.feat_pm + ((size_t)scene * P.n + i) * P.feat_stride : nullptr;
     float rel[3];
-    {
-      const float *pp = P.xyz + ((size_t)scene * P.n + i) * 3;
-      const float *qq = P.new_xyz + ((size_t)scene * P.npoint_total + j) * 3;
 #pragma unroll
-      for (int d = 0; d < 3; ++d) {
-        float v = pp[d] - qq[d];                       // pointnet2_utils.py:350
-        if (P.normalize_xyz) v = v / P.radius;         // :351-352, true division
-        rel[d] = v;
-      }
+    for (int d = 0; d < 3; ++d) {
+      float v = nx_pp[d] - nx_qq[d];                   // pointnet2_utils.py:350
+      if (P.normalize_xyz) v = v / P.radius;           // :351-352, true division
+      rel[d] = v;
+    }
+    // next tile: index and centre now, neighbour coordinates once the index has arrived
+    const int ntile = tile + tile_step;
+    int n_scene = 0, n_j = 0;
+    if (ntile < P.num_tiles) {
+      row_of(ntile, n_scene, n_j);
+      nx_i = __ldg(P.idx + ((size_t)n_scene * P.npoint_total + n_j) * ns + (tid % ns));
+#pragma unroll
+      for (int d = 0; d < 3; ++d) nx_qq[d] = __ldg(P.new_xyz + ((size_t)n_scene * P.npoint_total + n_j) * 3 + d);
     }
 
+    SA_TRACE(0)
     // ---- layer 1: gather K-chunks of A1 and accumulate D1 ------------------------------
-    for (int kc0 = 0; kc0 < P.k1pad; kc0 += kKChunk) {
-      const int kcn = min(kKChunk, P.k1pad - kc0);     // multiple of 16
+    // one 16-byte vector (8 channels) of this row: features, then xyz_rel, then zero padding
+    auto gather_q = [&](int k0, uint4 *dst) {
+      float f[8];
+      if (k0 + 8 <= P.c && P.feat_vec4) {
+        const float4 a = __ldg(reinterpret_cast<const float4 *>(frow + k0));
+        const float4 bq = __ldg(reinterpret_cast<const float4 *>(frow + k0 + 4));
+        f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w;
+        f[4] = bq.x; f[5] = bq.y; f[6] = bq.z; f[7] = bq.w;
+      } else {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          const int k = k0 + e;
+          float v = 0.f;
+          if (k < P.c) v = __ldg(frow + k);
+          else if (k < P.c + 3) v = (k - P.c == 0) ? rel[0] : ((k - P.c == 1) ? rel[1] : rel[2]);
+          f[e] = v;
+        }
+      }
+      *dst = make_uint4(pack2(f[0], f[1], P.fp16), pack2(f[2], f[3], P.fp16),
+                        pack2(f[4], f[5], P.fp16), pack2(f[6], f[7], P.fp16));
+    };
+    // with tail_sep the last 16 channels (k1pad % 128 == 16) live in their own buffer, so they are
+    // gathered together with the last full chunk and need no MMA round trip of their own
+    const int k_main = P.tail_sep ? P.k1pad - 16 : P.k1pad;
+    for (int kc0 = 0; kc0 < k_main; kc0 += kKChunk) {
+      const int kcn = min(kKChunk, k_main - kc0);      // multiple of 16
       const int nq = kcn / 8;
+      const bool last = kc0 + kKChunk >= k_main;
       // 16-byte-aligned all-feature chunks: 4 chunks (8 independent 16-byte loads) in flight
+      // (8 chunks in flight measured 1.8x SLOWER per tile: 10.8k vs 6.2k cycles at SA2)
       int q = 0;
       if (P.feat_vec4) {
         for (; q + 4 <= nq && kc0 + (q + 4) * 8 <= P.c; q += 4) {
@@ -201,30 +276,16 @@ sa_mlp_max_kernel(const SaParams P) {
                            pack2(hi[u].x, hi[u].y, P.fp16), pack2(hi[u].z, hi[u].w, P.fp16));
         }
       }
-      for (; q < nq; ++q) {
-        const int k0 = kc0 + q * 8;
-        float f[8];
-        if (k0 + 8 <= P.c && P.feat_vec4) {
-          const float4 a = __ldg(reinterpret_cast<const float4 *>(frow + k0));
-          const float4 bq = __ldg(reinterpret_cast<const float4 *>(frow + k0 + 4));
-          f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w;
-          f[4] = bq.x; f[5] = bq.y; f[6] = bq.z; f[7] = bq.w;
-        } else {
-#pragma unroll
-          for (int e = 0; e < 8; ++e) {
-            const int k = k0 + e;
-            float v = 0.f;
-            if (k < P.c) v = __ldg(frow + k);
-            else if (k < P.c + 3) v = (k - P.c == 0) ? rel[0] : ((k - P.c == 1) ? rel[1] : rel[2]);
-            f[e] = v;
-          }
-        }
-        ax[q * kRows + tid] = make_uint4(pack2(f[0], f[1], P.fp16), pack2(f[2], f[3], P.fp16),
-                                         pack2(f[4], f[5], P.fp16), pack2(f[6], f[7], P.fp16));
+      for (; q < nq; ++q) gather_q(kc0 + q * 8, &ax[q * kRows + tid]);
+      if (last && P.tail_sep) {
+        gather_q(k_main, &ax_tail[tid]);
+        gather_q(k_main + 8, &ax_tail[kRows + tid]);
       }
+      SA_TRACE(1)
       umma::fence_proxy_async_smem();
       umma::fence_before_sync();
       group_sync(group);
+      SA_TRACE(2)
       if (tid == 0) {
         umma::fence_after_sync();
         for (int ks = 0; ks < kcn / 16; ++ks) {
@@ -232,15 +293,27 @@ sa_mlp_max_kernel(const SaParams P) {
           const uint64_t bd = umma::smem_desc(w1_addr + (uint32_t)(kc0 / 8 + 2 * ks) * C1 * 16, C1 * 16, 128);
           umma::mma_bf16_ss(tmem_d1, ad, bd, kIdesc1, (kc0 | ks) != 0);
         }
+        if (last && P.tail_sep) {
+          const uint64_t ad = umma::smem_desc(ax_tail_addr, kRows * 16, 128);
+          const uint64_t bd = umma::smem_desc(w1_addr + (uint32_t)(k_main / 8) * C1 * 16, C1 * 16, 128);
+          umma::mma_bf16_ss(tmem_d1, ad, bd, kIdesc1, true);
+        }
         umma::commit(bar);
+      }
+      if (last && ntile < P.num_tiles) {
+        // the next tile's index arrived long ago: fetch its neighbour's coordinates under the MMAs
+#pragma unroll
+        for (int d = 0; d < 3; ++d) nx_pp[d] = __ldg(P.xyz + ((size_t)n_scene * P.n + nx_i) * 3 + d);
       }
       mbar_wait(bar, phase);
       phase ^= 1;
       umma::fence_after_sync();
+      SA_TRACE(3)
     }
 
     // ---- epilogue 1 -> X1 ; layer 2 ---------------------------------------------------
     epilogue_rows<C1>(tmem_d1, warp, tid, s_b1, ax, P.fp16);
+    SA_TRACE(4)
     umma::fence_proxy_async_smem();
     umma::fence_before_sync();
     group_sync(group);
@@ -258,8 +331,10 @@ sa_mlp_max_kernel(const SaParams P) {
     phase ^= 1;
     umma::fence_after_sync();
 
+    SA_TRACE(5)
     // ---- epilogue 2 -> X2 ; layer 3 (transposed: channels on lanes) ---------------------
     epilogue_rows<C2>(tmem_d2, warp, tid, s_b2, ax, P.fp16);
+    SA_TRACE(6)
     umma::fence_proxy_async_smem();
     umma::fence_before_sync();
     group_sync(group);
@@ -280,6 +355,7 @@ sa_mlp_max_kernel(const SaParams P) {
     phase ^= 1;
     umma::fence_after_sync();
 
+    SA_TRACE(7)
     // ---- epilogue 3: max over nsample columns, bias, ReLU, store -------------------------
 #pragma unroll
     for (int mt = 0; mt < C3 / 128; ++mt) {
@@ -287,12 +363,16 @@ sa_mlp_max_kernel(const SaParams P) {
       const float bias = s_b3[ch];
       float run = -INFINITY;
 #pragma unroll
-      for (int c0 = 0; c0 < kRows; c0 += 32) {
-        uint32_t v[32];
-        umma::ld_32x32b_x32(tmem_d3 + mt * 128 + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0, v);
+      for (int c0 = 0; c0 < kRows; c0 += 64) {
+        uint32_t va[32], vb[32];
+        umma::ld_32x32b_x32(tmem_d3 + mt * 128 + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0, va);
+        umma::ld_32x32b_x32(tmem_d3 + mt * 128 + ((uint32_t)(warp * 32) << 16) + (uint32_t)(c0 + 32), vb);
         umma::wait_ld();
+        uint32_t v[64];
 #pragma unroll
-        for (int g = 0; g < 32; g += 16) {              // nsample is a multiple of 16
+        for (int e = 0; e < 32; ++e) { v[e] = va[e]; v[32 + e] = vb[e]; }
+#pragma unroll
+        for (int g = 0; g < 64; g += 16) {              // nsample is a multiple of 16
           float m16 = __uint_as_float(v[g]);
 #pragma unroll
           for (int e = 1; e < 16; ++e) m16 = fmaxf(m16, __uint_as_float(v[g + e]));
@@ -308,6 +388,7 @@ sa_mlp_max_kernel(const SaParams P) {
         }
       }
     }
+    SA_TRACE(8)
     umma::fence_before_sync();
     group_sync(group);     // TMEM (D3T aliases D1/D2) and the A/X buffer are free again
     umma::fence_after_sync();
@@ -343,17 +424,35 @@ __global__ void pack_weight_kernel(int c_out, int c_in, int kpad, int xyz_first,
 }
 
 template <int C1, int C2, int C3>
-size_t sa_smem_bytes(int k1pad, int g) {
+size_t sa_smem_bytes(int k1pad, int g, bool tail_sep = false) {
   constexpr int kXVecs = (C1 > C2 ? C1 : C2) / 8 * kRows;
   constexpr int kAVecs = kKChunk / 8 * kRows;
   constexpr int kAXVecs = kXVecs > kAVecs ? kXVecs : kAVecs;
-  return 16 * ((size_t)g * kAXVecs + (size_t)(k1pad / 8) * C1 + (size_t)(C1 / 8) * C2 +
-               (size_t)(C2 / 8) * C3) + 4 * (C1 + C2 + C3) + 32;
+  return 16 * ((size_t)g * (kAXVecs + (tail_sep ? 2 * kRows : 0)) + (size_t)(k1pad / 8) * C1 +
+               (size_t)(C1 / 8) * C2 + (size_t)(C2 / 8) * C3) + 4 * (C1 + C2 + C3) + 32;
 }
 
 template <int C1, int C2, int C3, int G>
-int launch_sa_g(const SaParams &P, cudaStream_t stream) {
-  const size_t smem = sa_smem_bytes<C1, C2, C3>(P.k1pad, G);
+int sa_ctas_per_sm(size_t smem) {
+  // CTAs per SM: shared memory (228 KB per SM, 1 KB reserved per CTA) and TMEM (512 columns)
+  constexpr int kTmemCols = G * ((C1 + C2 > C3 ? C1 + C2 : C3) <= 128 ? 128 : 256);
+  const int per_sm = (int)((228 * 1024) / (smem + 1024));
+  return max(1, min(per_sm, 512 / kTmemCols));
+}
+
+template <int C1, int C2, int C3, int G>
+int launch_sa_g(SaParams P, cudaStream_t stream) {
+  size_t smem = sa_smem_bytes<C1, C2, C3>(P.k1pad, G);
+  // own buffer for a 16-channel K tail when it costs neither the launch nor a resident CTA
+  P.tail_sep = 0;
+  if (P.k1pad > 16 && P.k1pad % kKChunk == 16) {
+    const size_t with_tail = sa_smem_bytes<C1, C2, C3>(P.k1pad, G, true);
+    if (with_tail <= 227 * 1024 &&
+        sa_ctas_per_sm<C1, C2, C3, G>(with_tail) == sa_ctas_per_sm<C1, C2, C3, G>(smem)) {
+      P.tail_sep = 1;
+      smem = with_tail;
+    }
+  }
   if (smem > 227 * 1024)
     return set_error(BQA_ERR_UNSUPPORTED, "sa_mlp_max: needs %zu bytes of shared memory", smem);
   auto kern = sa_mlp_max_kernel<C1, C2, C3, G>;
@@ -361,12 +460,22 @@ int launch_sa_g(const SaParams &P, cudaStream_t stream) {
   int dev = 0, sms = 148;
   BQA_CUDA(cudaGetDevice(&dev));
   BQA_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-  // CTAs per SM: shared memory (228 KB per SM, 1 KB reserved per CTA) and TMEM (512 columns)
-  constexpr int kTmemCols = G * ((C1 + C2 > C3 ? C1 + C2 : C3) <= 128 ? 128 : 256);
-  int per_sm = (int)((228 * 1024) / (smem + 1024));
-  per_sm = max(1, min(per_sm, 512 / kTmemCols));
+  const int per_sm = sa_ctas_per_sm<C1, C2, C3, G>(smem);
   const int grid = min((P.num_tiles + G - 1) / G, sms * per_sm);
+#ifdef BQA_SA_TRACE
+  unsigned long long zeros[16] = {0};
+  cudaMemcpyToSymbol(g_sa_trace, zeros, sizeof(zeros));
+#endif
   kern<<<grid, G * kRows, smem, stream>>>(P);
+#ifdef BQA_SA_TRACE
+  unsigned long long t[16];
+  cudaMemcpyFromSymbol(t, g_sa_trace, sizeof(t));
+  const double tiles = (double)((P.num_tiles - 0 + grid * G - 1) / (grid * G));
+  fprintf(stderr, "[bqa sa trace] <%d,%d,%d,G=%d> c=%d ns=%d grid=%d tiles/pipeline=%.0f | cycles per tile: idx+xyz %.0f | "
+          "gather+pack %.0f | sync %.0f | mma1 %.0f | epi1 %.0f | sync+mma2 %.0f | epi2 %.0f | sync+mma3 %.0f | epi3 %.0f | "
+          "tail sync+loop %.0f\n", C1, C2, C3, G, P.c, P.nsample, grid, tiles, t[0] / tiles, t[1] / tiles, t[2] / tiles,
+          t[3] / tiles, t[4] / tiles, t[5] / tiles, t[6] / tiles, t[7] / tiles, t[8] / tiles, t[9] / tiles);
+#endif
   count_launch();
   return check_launch("sa_mlp_max_kernel");
 }
