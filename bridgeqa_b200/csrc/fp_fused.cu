@@ -34,15 +34,18 @@ constexpr int kChunk = 64;         // K per weight slice
 constexpr int kWidth = 256;        // C1 == C2 == 256 (both FP layers of the backbone)
 constexpr int kKnownTile = 512;    // known points staged per pass of three_nn
 
+// two fp32 -> one packed 16-bit pair in one instruction (fp16 saturates at +-65504; see sa_fused.cu)
 __device__ __forceinline__ uint32_t pack16(float lo, float hi, int fp16) {
-  if (fp16) {
-    lo = fminf(fmaxf(lo, -65504.f), 65504.f);
-    hi = fminf(fmaxf(hi, -65504.f), 65504.f);
-    __half2 v = __floats2half2_rn(lo, hi);
-    return *reinterpret_cast<uint32_t *>(&v);
-  }
-  __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
-  return *reinterpret_cast<uint32_t *>(&v);
+  uint32_t d;
+  if (fp16) asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+  else asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+  return d;
+}
+__device__ __forceinline__ uint32_t pack16_relu(float lo, float hi, int fp16) {
+  uint32_t d;
+  if (fp16) asm("cvt.rn.relu.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+  else asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+  return d;
 }
 
 __device__ __forceinline__ void bulk_load(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar) {
@@ -231,9 +234,9 @@ fp_mlp_kernel(const FpParams P) {
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
               const int col = c0 + q * 8 + e * 2;
-              const float lo = fmaxf(__uint_as_float(v[q * 8 + e * 2]) + s_b1[col], 0.f);
-              const float hi = fmaxf(__uint_as_float(v[q * 8 + e * 2 + 1]) + s_b1[col + 1], 0.f);
-              p[e] = pack16(lo, hi, P.fp16);
+              const float lo = __uint_as_float(v[q * 8 + e * 2]) + s_b1[col];
+              const float hi = __uint_as_float(v[q * 8 + e * 2 + 1]) + s_b1[col + 1];
+              p[e] = pack16_relu(lo, hi, P.fp16);
             }
             x1[(c0 / 8 + q) * kRows + tid] = make_uint4(p[0], p[1], p[2], p[3]);
           }

@@ -40,17 +40,20 @@ namespace {
 constexpr int kRows = 128;       // rows per tile == threads per CTA
 constexpr int kKChunk = 128;     // layer-1 K processed per pass
 
-// two fp32 -> one packed 16-bit pair.  fp16 mode saturates at +-65504 instead of producing
-// inf (bf16 has fp32's range and needs no clamp).
+// two fp32 -> one packed 16-bit pair, ONE instruction (SASS F2FP...PACK_AB).  fp16 mode saturates
+// at +-65504 instead of producing inf (bf16 has fp32's range and needs no clamp); the _relu form
+// folds max(x, 0) into the conversion.
 __device__ __forceinline__ uint32_t pack2(float lo, float hi, int fp16) {
-  if (fp16) {
-    lo = fminf(fmaxf(lo, -65504.f), 65504.f);
-    hi = fminf(fmaxf(hi, -65504.f), 65504.f);
-    __half2 v = __floats2half2_rn(lo, hi);
-    return *reinterpret_cast<uint32_t *>(&v);
-  }
-  __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
-  return *reinterpret_cast<uint32_t *>(&v);
+  uint32_t d;
+  if (fp16) asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+  else asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+  return d;
+}
+__device__ __forceinline__ uint32_t pack2_relu(float lo, float hi, int fp16) {
+  uint32_t d;
+  if (fp16) asm("cvt.rn.relu.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+  else asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+  return d;
 }
 
 struct SaParams {
@@ -93,9 +96,9 @@ __device__ __forceinline__ void epilogue_rows(uint32_t tmem_d, int warp, int row
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
         const int col = c0 + q * 8 + e * 2;
-        const float lo = fmaxf(__uint_as_float(v[q * 8 + e * 2]) + s_bias[col], 0.f);
-        const float hi = fmaxf(__uint_as_float(v[q * 8 + e * 2 + 1]) + s_bias[col + 1], 0.f);
-        p[e] = pack2(lo, hi, fp16);
+        const float lo = __uint_as_float(v[q * 8 + e * 2]) + s_bias[col];
+        const float hi = __uint_as_float(v[q * 8 + e * 2 + 1]) + s_bias[col + 1];
+        p[e] = pack2_relu(lo, hi, fp16);                 // relu(D + b), rounded once
       }
       x_buf[(c0 / 8 + q) * kRows + row] = make_uint4(p[0], p[1], p[2], p[3]);
     }
