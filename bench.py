@@ -120,6 +120,19 @@ class ClockSampler(object):
 
 # ------------------------------------------------------------------ reference (CPU) ---
 
+def rank_sm_clock(index):
+    """Current SM clock (MHz) of GPU `index` through NVML; -1 when NVML is not usable."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        phys = int(vis.split(",")[index]) if vis and vis.split(",")[index].isdigit() else index
+        h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+        return float(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM))
+    except Exception:
+        return -1.0
+
+
 def cpu_reference_run(steps, warmup, sample_scenes, threads=None):
     """The reference path re-expressed on the host (the reference ops are CUDA-only,
     sampling.cpp:83): C oracle ops + torch-CPU conv/BN, all host threads.  Each step is a
@@ -416,8 +429,11 @@ def main():
     ev1 = torch.cuda.Event(enable_timing=True)
     ev0.record()
     t_host0 = time.perf_counter()
+    my_sm_mhz = -1.0
     for i in range(args.steps):
         step(i)
+        if i == args.steps // 2:
+            my_sm_mhz = rank_sm_clock(local_rank)     # this rank's GPU, mid-run (NVML, host side only)
     host_issue_ms = (time.perf_counter() - t_host0) * 1e3 / args.steps
     ev1.record()
     barrier()
@@ -518,12 +534,14 @@ def main():
     e2e_ms = e0.elapsed_time(e1)
 
     # max over ranks
-    t = torch.tensor([elapsed_ms, e2e_ms], dtype=torch.float64, device=device)
+    t = torch.tensor([elapsed_ms, e2e_ms, my_sm_mhz], dtype=torch.float64, device=device)
     by_rank = [elapsed_ms / args.steps]
+    mhz_by_rank = [my_sm_mhz]
     if world > 1:
         every = [torch.zeros_like(t) for _ in range(world)]
         dist.all_gather(every, t)
         by_rank = [float(x[0]) / args.steps for x in every]       # device time of each rank's K steps
+        mhz_by_rank = [float(x[2]) for x in every]
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     elapsed_ms, e2e_ms = float(t[0]), float(t[1])
 
@@ -595,6 +613,7 @@ def main():
             "e2e": {"value": scenes / (e2e_ms / 1e3), "unit": UNIT, "ms_per_step": e2e_ms / args.steps,
                     "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes},
             "ms_per_step_by_rank": [round(v, 4) for v in by_rank],
+            "sm_mhz_by_rank": mhz_by_rank,
             "gpu_launches": launches,
             "host_issue_ms_per_step": round(host_issue_ms, 3),
             "kernel_pass": {"ms_per_step": round(kernel_pass_ms / args.steps, 4),
