@@ -28,6 +28,7 @@ _SIGNATURES = {
     "bqa_furthest_point_sampling": ([_I, _I, _I, _P, _P, _P, _P, _P], _I),
     "bqa_furthest_point_sampling_slice": ([_I, _I, _I, _I, _I, _P, _P, _P, _P, _I, _P], _I),
     "bqa_group_concat_point_major": ([_I, _I, _I, _I, _I, _I, _P, _P, _P, _P, _F, _I, _P, _P], _I),
+    "bqa_nn_distance": ([_I, _I, _I, _P, _P, _I, _F, _P, _P, _P, _P, _P], _I),
     "bqa_bn_relu_max_supported": ([_I], _I),
     "bqa_bn_train_stats": ([_I, _I, _LL, _P, _P, _F, _F, _P, _P, _P, _P, _P], _I),
     "bqa_bn_relu_forward": ([_I, _I, _LL, _P, _P, _P, _P, _P, _P, _P], _I),

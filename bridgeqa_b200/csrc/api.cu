@@ -43,6 +43,8 @@ int ref_opt_n_threads(int work_size) {
 int fps_dispatch(int b, int n, int m, int j_begin, int j_end, const float *xyz, int *idxs,
                  float *new_xyz, float *scratch, bool exclusive, const int *run_flags,
                  cudaStream_t stream);
+int nn_distance_dispatch(int b, int n, int m, int mode, float delta, const float *pc1, const float *pc2,
+                         float *dist1, long long *idx1, float *dist2, long long *idx2, cudaStream_t stream);
 bool bn_relu_max_supported(int ns);
 int bn_stats_dispatch(int b, int c, long long l, const float *y, double *sums, float eps, float momentum,
                       float *mean, float *invstd, float *running_mean, float *running_var,
@@ -386,6 +388,16 @@ int bqa_fp_mlp_forward(int b, int n, int m, int c_known, int c_skip, const float
   return fp_forward_dispatch(b, n, m, c_known, c_skip, unknown, known, known_feat, known_stride,
                              skip_feat, skip_stride, c1, c2, w, b1, b2, out_cm, out_pm, precision,
                              (cudaStream_t)stream);
+}
+
+int bqa_nn_distance(int b, int n, int m, const float *pc1, const float *pc2, int mode, float delta,
+                    float *dist1, long long *idx1, float *dist2, long long *idx2, void *stream) {
+  NONNEG(b); NONNEG(n); NONNEG(m);
+  BQA_REQUIRE(mode >= 0 && mode <= 2, "%s: mode must be 0 (squared L2), 1 (L1) or 2 (Huber)", __func__);
+  if (b == 0 || (n == 0 && m == 0)) return BQA_OK;
+  BQA_REQUIRE(n > 0 && m > 0, "%s: both point sets must be non-empty (torch.min over an empty axis raises)", __func__);
+  PTR(pc1); PTR(pc2); PTR(dist1); PTR(idx1); PTR(dist2); PTR(idx2);
+  return nn_distance_dispatch(b, n, m, mode, delta, pc1, pc2, dist1, idx1, dist2, idx2, (cudaStream_t)stream);
 }
 
 #define ALIGNED16(p) BQA_REQUIRE((reinterpret_cast<uintptr_t>(p) & 15) == 0, "%s: %s must be 16-byte aligned", __func__, #p)

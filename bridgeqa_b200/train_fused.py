@@ -116,7 +116,7 @@ class _BNReLUMax(Function):
 def norm_supported(norm, y):
     return (enabled() and norm.training and y.is_cuda and y.dtype == _f32 and norm.affine
             and norm.momentum is not None and y.dim() >= 3 and y.numel() > 0
-            and y.numel() // y.shape[1] > 1)
+            and y.numel() // y.shape[1] > 1 and y.shape[0] <= 65535 and y.shape[1] <= 65535)
 
 
 def bn_relu(y, norm):
@@ -125,7 +125,9 @@ def bn_relu(y, norm):
 
 
 def max_supported(y):
-    return y.dim() == 4 and bool(N.lib().bqa_bn_relu_max_supported(int(y.shape[3])))
+    # (the kernels index one (b, c) row per blockIdx.y)
+    return (y.dim() == 4 and y.shape[0] * y.shape[1] <= 65535
+            and bool(N.lib().bqa_bn_relu_max_supported(int(y.shape[3]))))
 
 
 def bn_relu_max(y, norm):

@@ -231,6 +231,14 @@ BQA_API int bqa_fp_mlp_forward(int b, int n, int m, int c_known, int c_skip, con
                                const void *w, const float *b1, const float *b2, float *out_cm,
                                float *out_pm, int precision, void *stream);
 
+/* ---- nn_distance (first consumer of the hot path's outputs) -------------
+ * replaces: utils/nn_distance.py:25-52 `nn_distance(pc1 (B,N,3), pc2 (B,M,3), l1smooth, delta, l1)`
+ *           -> dist1 (B,N) f32, idx1 (B,N) i64, dist2 (B,M) f32, idx2 (B,M) i64, as used by the
+ *           VoteNet losses (lib/loss_helper.py:66,91,144).  mode 0: sum of squares, 1: L1, 2: Huber.
+ * One pass, no (B,N,M,3) tensor; bit-identical to the torch expression on the GPU.  */
+BQA_API int bqa_nn_distance(int b, int n, int m, const float *pc1, const float *pc2, int mode, float delta,
+                            float *dist1, long long *idx1, float *dist2, long long *idx2, void *stream);
+
 /* ---- train-mode BatchNorm + ReLU (+ max over nsample) --------------------------------------
  * replaces, in model.train(), the nn.BatchNorm2d (training=True) + shared nn.ReLU that follow
  * every 1x1 conv of a SharedMLP block (lib/pointnet2/pytorch_utils.py:11-36, 73-80) and, for the
