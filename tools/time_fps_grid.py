@@ -28,7 +28,7 @@ def timeit(fn, warm=3, it=15):
 print("BQA_FPS_SORTED_CS =", os.environ.get("BQA_FPS_SORTED_CS"))
 for b, n, m in [(16, 40000, 2048), (8, 40000, 2048), (16, 20000, 2048), (16, 100000, 2048), (64, 40000, 2048)]:
     xyz = synthetic.make_batch(b, n, 0)[..., :3].contiguous().cuda()
-    grid = fused.prebuild_ball_query_grid(xyz, 0.2, inline=True)
+    R = float(os.environ.get("GRID_R", "0.2")); grid = fused.prebuild_ball_query_grid(xyz, R, inline=True)
     t_plain = timeit(lambda: ext.furthest_point_sampling(xyz, m, return_xyz=True))
     t_build = timeit(lambda: fused.prebuild_ball_query_grid(xyz, 0.2, inline=True))
     t_sorted = timeit(lambda: fused.furthest_point_sample_grid(xyz, m, grid))
