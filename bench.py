@@ -218,7 +218,7 @@ def algorithmic_work(name, dims):
     if name == "bqa_ball_query_grid_build":
         b, n = dims[:2]
         return {"bytes": b * (12 * n + 16 * n), "bound": "hbm"}       # read xyz, write the cell-sorted float4 copy
-    if name in ("bqa_group_points", "bqa_group_points_grad"):
+    if name in ("bqa_group_points", "bqa_group_points_grad", "bqa_group_points_grad_ws"):
         b, c, n, npt, ns = dims[:5]
         return {"bytes": b * (4 * npt * ns + 8 * c * npt * ns), "bound": "hbm"}
     if name in ("bqa_gather_points", "bqa_gather_points_grad"):

@@ -27,6 +27,8 @@ _SIGNATURES = {
     "bqa_fps_scratch_bytes": ([_I, _I], _LL),
     "bqa_furthest_point_sampling": ([_I, _I, _I, _P, _P, _P, _P, _P], _I),
     "bqa_furthest_point_sampling_slice": ([_I, _I, _I, _I, _I, _P, _P, _P, _P, _I, _P], _I),
+    "bqa_group_points_grad_workspace_bytes": ([_I, _I, _I], _LL),
+    "bqa_group_points_grad_ws": ([_I, _I, _I, _I, _I, _P, _P, _P, _P, _P], _I),
     "bqa_group_concat_point_major": ([_I, _I, _I, _I, _I, _I, _P, _P, _P, _P, _F, _I, _P, _P], _I),
     "bqa_nn_distance": ([_I, _I, _I, _P, _P, _I, _F, _P, _P, _P, _P, _P], _I),
     "bqa_bn_relu_max_supported": ([_I], _I),

@@ -84,6 +84,9 @@ int gather_rows_dispatch(int b, int c, int n, long long e_total, const float *po
 int scatter_add_rows_dispatch(int b, int c, int n, long long e_total, const float *grad_out,
                               const int *idx, float *grad_points, cudaStream_t stream);
 int transpose_cn_dispatch(int b, int c, int n, const float *in, float *out, cudaStream_t stream);
+long long scatter_add_workspace_bytes(int b, int c, int n);
+int scatter_add_rows_ws_dispatch(int b, int c, int n, long long e_total, const float *grad_out, const int *idx,
+                                 float *grad_points, float *acc, cudaStream_t stream);
 int group_concat_pm_dispatch(int b, int n, int c, int feat_stride, long long e_total, int nsample, float radius,
                              int normalize, const float *xyz, const float *new_xyz, const float *feat,
                              const int *idx, float *out, cudaStream_t stream);
@@ -259,6 +262,23 @@ int bqa_group_points(int b, int c, int n, int npoints, int nsample, const float 
   if ((long long)b * c * e == 0) return BQA_OK;
   PTR(points); PTR(idx); PTR(out);
   return gather_rows_dispatch(b, c, n, e, points, idx, out, (cudaStream_t)stream);
+}
+
+long long bqa_group_points_grad_workspace_bytes(int b, int c, int n) {
+  if (b <= 0 || c <= 0 || n <= 0) return 0;
+  return scatter_add_workspace_bytes(b, c, n);
+}
+
+int bqa_group_points_grad_ws(int b, int c, int n, int npoints, int nsample, const float *grad_out,
+                             const int *idx, float *grad_points, void *workspace, void *stream) {
+  NONNEG(b); NONNEG(c); NONNEG(n); NONNEG(npoints); NONNEG(nsample);
+  if ((long long)b * c * n == 0) return BQA_OK;
+  PTR(grad_points); PTR(workspace);
+  const long long e = (long long)npoints * nsample;
+  if (e > 0) { PTR(grad_out); PTR(idx); }
+  BQA_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 15) == 0, "%s: workspace must be 16-byte aligned", __func__);
+  return scatter_add_rows_ws_dispatch(b, c, n, e, grad_out, idx, grad_points, (float *)workspace,
+                                      (cudaStream_t)stream);
 }
 
 int bqa_group_concat_point_major(int b, int n, int c, int feat_stride, int npoint, int nsample,

@@ -70,11 +70,27 @@ bn_stats_kernel(int c, long long l, const float *__restrict__ y, double *__restr
   float s1 = 0.f, s2 = 0.f;
   if ((l & 3) == 0) {
     const float4 *r4 = reinterpret_cast<const float4 *>(row);
-    for (long long i = i0 / 4 + threadIdx.x; i < i1 / 4; i += kThreads) {
-      const float4 v = __ldg(r4 + i);
-      s1 += (v.x + v.y) + (v.z + v.w);
-      s2 += (v.x * v.x + v.y * v.y) + (v.z * v.z + v.w * v.w);
+    // 4 independent 16-byte loads in flight per thread, 4 accumulator pairs
+    float a1[4] = {0.f, 0.f, 0.f, 0.f}, a2[4] = {0.f, 0.f, 0.f, 0.f};
+    long long i = i0 / 4 + threadIdx.x;
+    const long long e4 = i1 / 4;
+    for (; i + 3 * kThreads < e4; i += 4 * kThreads) {
+      float4 v[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) v[u] = __ldg(r4 + i + u * kThreads);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        a1[u] += (v[u].x + v[u].y) + (v[u].z + v[u].w);
+        a2[u] += (v[u].x * v[u].x + v[u].y * v[u].y) + (v[u].z * v[u].z + v[u].w * v[u].w);
+      }
     }
+    for (; i < e4; i += kThreads) {
+      const float4 v = __ldg(r4 + i);
+      a1[0] += (v.x + v.y) + (v.z + v.w);
+      a2[0] += (v.x * v.x + v.y * v.y) + (v.z * v.z + v.w * v.w);
+    }
+    s1 = (a1[0] + a1[1]) + (a1[2] + a1[3]);
+    s2 = (a2[0] + a2[1]) + (a2[2] + a2[3]);
   } else {
     for (long long i = i0 + threadIdx.x; i < i1; i += kThreads) {
       const float v = __ldg(row + i);

@@ -51,6 +51,46 @@ scatter_add_rows_kernel(int c, int n, int e_total, const float *__restrict__ gra
   }
 }
 
+// Same scatter-add through a POINT-MAJOR accumulator acc (b, n, c4) (c4 = c rounded up to 4):
+// four channels of one point are contiguous there, so one vector reduction
+// (red.global.add.v4.f32, sm_90+) replaces four scalar atomics -- the scatter is bound by the
+// number of L2 reduction operations (each source point receives ~nsample/2 adds per channel).
+// A transpose then writes grad_points (b, c, n); it needs no zero-fill.
+__global__ void __launch_bounds__(kThreads)
+scatter_add_pm_kernel(int c, int c4, int n, int e_total, const float *__restrict__ grad_out,
+                      const int *__restrict__ idx, float *__restrict__ acc) {
+  const int scene = blockIdx.z;
+  const int l0 = blockIdx.y * 4;
+  const int e = blockIdx.x * kThreads + threadIdx.x;
+  if (e >= e_total) return;
+  const int a = idx[(size_t)scene * e_total + e];
+  float v[4];
+#pragma unroll
+  for (int u = 0; u < 4; ++u)
+    v[u] = (l0 + u < c) ? grad_out[((size_t)scene * c + l0 + u) * e_total + e] : 0.f;
+  float *dst = acc + ((size_t)scene * n + a) * c4 + l0;
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3])
+               : "memory");
+}
+
+// acc (b, n, c4) -> out (b, c, n), dropping the padding channels
+__global__ void __launch_bounds__(256)
+transpose_nc_kernel(int c, int c4, int n, const float *__restrict__ acc, float *__restrict__ out) {
+  __shared__ float tile[32][33];
+  const int scene = blockIdx.z;
+  const int n0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
+  for (int r = ty; r < 32; r += 8) {
+    const int nn = n0 + r, cc = c0 + tx;
+    tile[r][tx] = (nn < n && cc < c4) ? acc[((size_t)scene * n + nn) * c4 + cc] : 0.f;
+  }
+  __syncthreads();
+  for (int r = ty; r < 32; r += 8) {
+    const int cc = c0 + r, nn = n0 + tx;
+    if (cc < c && nn < n) out[((size_t)scene * c + cc) * n + nn] = tile[tx][r];
+  }
+}
+
 // (b,c,n) -> (b,n,c) through a 32x32 shared tile (both sides coalesced)
 __global__ void __launch_bounds__(256)
 transpose_cn_kernel(int c, int n, const float *__restrict__ in, float *__restrict__ out) {
@@ -139,6 +179,30 @@ int scatter_add_rows_dispatch(int b, int c, int n, long long e_total, const floa
   scatter_add_rows_kernel<<<grid, kThreads, 0, stream>>>(c, n, (int)e_total, grad_out, idx, grad_points);
   count_launch();
   return check_launch("scatter_add_rows_kernel");
+}
+
+long long scatter_add_workspace_bytes(int b, int c, int n) {
+  return 4ll * b * n * ((c + 3) / 4 * 4);
+}
+
+// scatter_add_rows_dispatch with a caller-provided accumulator of scatter_add_workspace_bytes()
+int scatter_add_rows_ws_dispatch(int b, int c, int n, long long e_total, const float *grad_out, const int *idx,
+                                 float *grad_points, float *acc, cudaStream_t stream) {
+  if (b == 0 || c == 0 || n == 0) return BQA_OK;
+  const int c4 = (c + 3) / 4 * 4;
+  BQA_CUDA(cudaMemsetAsync(acc, 0, sizeof(float) * (size_t)b * n * c4, stream));
+  if (e_total > 0) {
+    if (ceil_div_ll(e_total, kThreads) > 2147483647ll || c4 / 4 > 65535 || b > 65535)
+      return set_error(BQA_ERR_UNSUPPORTED, "group grad: grid too large (e=%lld c=%d b=%d)", e_total, c, b);
+    dim3 grid((unsigned)ceil_div_ll(e_total, kThreads), (unsigned)(c4 / 4), (unsigned)b);
+    scatter_add_pm_kernel<<<grid, kThreads, 0, stream>>>(c, c4, n, (int)e_total, grad_out, idx, acc);
+    count_launch();
+    if (int rc = check_launch("scatter_add_pm_kernel")) return rc;
+  }
+  dim3 tg((unsigned)ceil_div(n, 32), (unsigned)ceil_div(c, 32), (unsigned)b);
+  transpose_nc_kernel<<<tg, 256, 0, stream>>>(c, c4, n, acc, grad_points);
+  count_launch();
+  return check_launch("transpose_nc_kernel");
 }
 
 int transpose_cn_dispatch(int b, int c, int n, const float *in, float *out, cudaStream_t stream) {

@@ -116,14 +116,21 @@ def group_concat_point_major(xyz, new_xyz, feat_pm, idx, radius, normalize_xyz):
 
 
 def group_points_grad(grad_out, idx, n):
-    """group_points.cpp:38-62.  grad_out (B,C,M,S), idx (B,M,S) -> (B,C,n)."""
+    """group_points.cpp:38-62.  grad_out (B,C,M,S), idx (B,M,S) -> (B,C,n).  Wide tensors go through
+    the point-major accumulator (vector reductions, bqa_group_points_grad_ws)."""
     N.check_tensor(grad_out, "grad_out", _f32)
     N.check_tensor(idx, "idx", _i32)
     b, c, npoints, nsample = grad_out.shape
     out = torch.empty((b, c, int(n)), dtype=_f32, device=grad_out.device)
     with _guard(grad_out):
-        N.call("bqa_group_points_grad", b, c, int(n), npoints, nsample, N.ptr(grad_out),
-               N.ptr(idx), N.ptr(out), N.stream_ptr(grad_out.device))
+        if c >= 8:
+            nbytes = N.lib().bqa_group_points_grad_workspace_bytes(b, c, int(n))
+            work = torch.empty((max(nbytes, 16) // 4,), dtype=_f32, device=grad_out.device)
+            N.call("bqa_group_points_grad_ws", b, c, int(n), npoints, nsample, N.ptr(grad_out),
+                   N.ptr(idx), N.ptr(out), N.ptr(work), N.stream_ptr(grad_out.device))
+        else:
+            N.call("bqa_group_points_grad", b, c, int(n), npoints, nsample, N.ptr(grad_out),
+                   N.ptr(idx), N.ptr(out), N.stream_ptr(grad_out.device))
     return out
 
 

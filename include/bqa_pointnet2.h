@@ -139,6 +139,14 @@ BQA_API int bqa_ball_query_grid_search(int b, int n, int m_total, int j_begin, i
  * points (b,c,n), idx (b,npoints,nsample) -> out (b,c,npoints,nsample) */
 BQA_API int bqa_group_points(int b, int c, int n, int npoints, int nsample, const float *points,
                      const int *idx, float *out, void *stream);
+/* group_points_grad through a point-major accumulator (workspace of
+ * bqa_group_points_grad_workspace_bytes(b,c,n) bytes, 16-byte aligned): one vector reduction per
+ * 4 channels instead of 4 scalar atomics, then a transpose into grad_points (b,c,n).  Same result
+ * as bqa_group_points_grad up to the order of the floating-point additions (both use atomics). */
+BQA_API long long bqa_group_points_grad_workspace_bytes(int b, int c, int n);
+BQA_API int bqa_group_points_grad_ws(int b, int c, int n, int npoints, int nsample, const float *grad_out,
+                                     const int *idx, float *grad_points, void *workspace, void *stream);
+
 /* QueryAndGroup.forward after the ball query (pointnet2_utils.py:347-359: group xyz, subtract the
  * centre, optionally divide by the radius, group the features, cat) in ONE pass, for a point-major
  * feature source feat_pm (b, n, feat_stride) -- e.g. the (B,N,3+C) input cloud itself:
