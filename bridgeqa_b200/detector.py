@@ -173,15 +173,21 @@ class Pointnet2Backbone(nn.Module):
             outs = []
             flags = None
             for k, sa in enumerate((self.sa1, self.sa2, self.sa3, self.sa4)):
-                inds = new_xyz = None
-                if k >= 1 and xyz.is_cuda and self.prefix_check and not xyz.requires_grad:
+                inds = new_xyz = grid = None
+                plain = xyz.is_cuda and not xyz.requires_grad
+                if k == 0 and plain and self.fps_grid and fused.enabled() \
+                        and fused.fps_grid_supported(xyz.size(1), sa.npoint):
+                    # SA1: one cell grid serves the pruned sampling and the ball query
+                    grid = fused.prebuild_ball_query_grid(xyz, sa.radius, inline=True)
+                    inds, new_xyz = fused.furthest_point_sample_grid(xyz, sa.npoint, grid)
+                if k >= 1 and plain and self.prefix_check:
                     if k == 1 and 0 < sa.npoint <= min(xyz.size(1), 8192):
                         flags = fused.fps_prefix_check(xyz, sa.npoint)
                     if flags is not None and sa.npoint <= min(self.sa2.npoint, xyz.size(1)):
                         inds, new_xyz = fused.furthest_point_sample_cond(xyz, sa.npoint, flags)
                     else:
                         flags = None
-                xyz, features, inds = sa(xyz, features, inds, new_xyz=new_xyz)
+                xyz, features, inds = sa(xyz, features, inds, new_xyz=new_xyz, grid=grid)
                 outs.append((xyz, features, inds))
         data_dict["sa1_xyz"], data_dict["sa1_features"], data_dict["sa1_inds"] = outs[0]
         data_dict["sa2_xyz"], data_dict["sa2_features"], data_dict["sa2_inds"] = outs[1]

@@ -221,6 +221,22 @@ def furthest_point_sample_grid(xyz, npoint, grid):
     return inds, new_xyz
 
 
+def ball_query_on_grid(new_xyz, xyz, radius, nsample, grid):
+    """ball_query(new_xyz, xyz, radius, nsample) over a prebuilt cell grid (buffer, event | None)."""
+    N.check_tensor(xyz, "xyz", _f32)
+    N.check_tensor(new_xyz, "new_xyz", _f32)
+    b, n, _ = xyz.shape
+    npoint = new_xyz.size(1)
+    if grid[1] is not None:
+        torch.cuda.current_stream(xyz.device).wait_event(grid[1])
+    idx = torch.empty((b, npoint, int(nsample)), dtype=torch.int32, device=xyz.device)
+    with torch.cuda.device(xyz.device):
+        N.call("bqa_ball_query_grid_search", b, n, npoint, 0, npoint, ctypes.c_float(radius),
+               int(nsample), N.ptr(new_xyz), N.ptr(xyz), N.ptr(idx), N.ptr(grid[0]),
+               N.stream_ptr(xyz.device))
+    return idx
+
+
 def sa_forward(xyz, new_xyz, features, radius, nsample, normalize_xyz, packed, grid=None):
     """-> new_features (B, C3, npoint) fp32, with a point-major twin attached as ._bqa_pm.
     `grid`: optional (buffer, event) from prebuild_ball_query_grid(xyz, ...)."""
@@ -229,13 +245,7 @@ def sa_forward(xyz, new_xyz, features, radius, nsample, normalize_xyz, packed, g
     b, n, _ = xyz.shape
     npoint = new_xyz.size(1)
     if grid is not None:
-        if grid[1] is not None:
-            torch.cuda.current_stream(xyz.device).wait_event(grid[1])
-        idx = torch.empty((b, npoint, int(nsample)), dtype=torch.int32, device=xyz.device)
-        with torch.cuda.device(xyz.device):
-            N.call("bqa_ball_query_grid_search", b, n, npoint, 0, npoint, ctypes.c_float(radius),
-                   int(nsample), N.ptr(new_xyz), N.ptr(xyz), N.ptr(idx), N.ptr(grid[0]),
-                   N.stream_ptr(xyz.device))
+        idx = ball_query_on_grid(new_xyz, xyz, radius, nsample, grid)
     else:
         idx = _ext.ball_query(new_xyz, xyz, radius, nsample)
     if features is not None:

@@ -177,7 +177,10 @@ class PointnetSAModuleVotes(nn.Module):
                                             self.normalize_xyz, self._packed(), grid=grid)
             return new_xyz, new_features, inds
 
-        grouped = self.grouper(xyz, new_xyz, features)
+        if grid is not None and isinstance(self.grouper, pointnet2_utils.QueryAndGroup):
+            grouped = self.grouper(xyz, new_xyz, features, grid=grid)
+        else:
+            grouped = self.grouper(xyz, new_xyz, features)
         unique_cnt = grouped[2] if self.ret_unique_cnt else None
         grouped_features, grouped_xyz = grouped[0], grouped[1]
 

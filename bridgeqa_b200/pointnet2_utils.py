@@ -172,8 +172,14 @@ class QueryAndGroup(nn.Module):
                 idx[b, r] = torch.cat((uniq, uniq[pick]))
         return counts
 
-    def forward(self, xyz, new_xyz, features=None):
-        idx = ball_query(self.radius, self.nsample, xyz, new_xyz)
+    def forward(self, xyz, new_xyz, features=None, grid=None):
+        """`grid` (optional, beyond the reference signature): a cell grid already built for `xyz`
+        (fused.prebuild_ball_query_grid), e.g. the one the sampling just used."""
+        if grid is not None:
+            from . import fused
+            idx = fused.ball_query_on_grid(new_xyz.detach(), xyz.detach(), self.radius, self.nsample, grid)
+        else:
+            idx = ball_query(self.radius, self.nsample, xyz, new_xyz)
         unique_cnt = self._resample_uniformly(idx) if self.sample_uniformly else None
 
         # one-pass grouping + centring + cat straight from a point-major twin of the features
