@@ -419,6 +419,7 @@ def main():
     clocks = ClockSampler(local_rank)
     if rank == 0:
         clocks.start()
+    rank_sm_clock(local_rank)          # NVML initialised here, not inside the timed region
     for i in range(max(args.warmup, ROT if not args.no_graph else 0)):   # every input buffer's graph exists
         step(i)
     barrier()
