@@ -30,6 +30,7 @@
 #include <cuda_fp16.h>
 
 #include <cstdio>
+#include <cstdlib>
 
 #include "common.cuh"
 #include "tcgen05.cuh"
@@ -76,12 +77,14 @@ struct SaParams {
 
 // epilogue of a row-on-lane accumulator: X[r][0..CN) = relu(D[r][*] + bias) as bf16, stored
 // chunk-major ([CN/8][128] x 16 B) for the next MMA.
+// CB..CE: the column range this thread converts (a pipeline of 8 warps splits the columns of a row
+// between warp w and warp w + 4, which both reach TMEM lane quarter w)
 template <int CN>
 __device__ __forceinline__ void epilogue_rows(uint32_t tmem_d, int warp, int row, const float *s_bias,
-                                              uint4 *x_buf, int fp16) {
+                                              uint4 *x_buf, int fp16, int cb, int ce) {
   static_assert(CN % 64 == 0, "two 32-column TMEM loads per step");
-#pragma unroll
-  for (int c0 = 0; c0 < CN; c0 += 64) {
+#pragma unroll 1
+  for (int c0 = cb; c0 < ce; c0 += 64) {
     // two tcgen05.ld in flight, one wait: the load latency is paid once per 64 columns
     uint32_t va[32], vb[32];
     umma::ld_32x32b_x32(tmem_d + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0, va);
@@ -114,18 +117,24 @@ __device__ unsigned long long g_sa_trace[16];
 #define SA_TRACE(i)
 #endif
 
-// named barrier over the 128 threads of one tile pipeline (id 1 or 2; 0 is __syncthreads)
+// named barrier over the threads of one tile pipeline (id 1 or 2; 0 is __syncthreads)
+template <int THREADS>
 __device__ __forceinline__ void group_sync(int group) {
-  asm volatile("bar.sync %0, 128;" ::"r"(group + 1) : "memory");
+  asm volatile("bar.sync %0, %1;" ::"r"(group + 1), "n"(THREADS) : "memory");
 }
 
 // Two independent tile pipelines per CTA (threads 0-127 and 128-255) share one copy of the
 // weights in shared memory; each has its own A/X buffer, mbarrier and TMEM columns, so the
 // gather / epilogue of one tile overlaps the MMAs of the other.
-template <int C1, int C2, int C3, int G>
-__global__ void __launch_bounds__(G * kRows)
+// W = warps per pipeline: 4 (thread = row) or 8 (two threads per row: warp w and warp w + 4 share TMEM
+// lane quarter w and split the row's gather chunks and epilogue columns, which halves the two
+// longest latency chains of a tile).
+template <int C1, int C2, int C3, int G, int W>
+__global__ void __launch_bounds__(G * W * 32)
 sa_mlp_max_kernel(const SaParams P) {
   static_assert(G == 1 || G == 2, "one or two tile pipelines per CTA");
+  static_assert(W == 4 || W == 8, "4 or 8 warps per pipeline");
+  constexpr int kPT = W * 32;                                         // threads per pipeline
   static_assert(C1 % 32 == 0 && C2 % 32 == 0 && C3 % 128 == 0, "channel counts");
   constexpr int kXVecs = (C1 > C2 ? C1 : C2) / 8 * kRows;             // X1 / X2 buffer
   constexpr int kAVecs = kKChunk / 8 * kRows;                         // layer-1 A chunk
@@ -146,19 +155,21 @@ sa_mlp_max_kernel(const SaParams P) {
   uint64_t *s_bar = reinterpret_cast<uint64_t *>(s_b3 + C3);          // one per pipeline
   uint32_t *s_tmem = reinterpret_cast<uint32_t *>(s_bar + 2);
 
-  const int group = threadIdx.x >> 7;       // pipeline 0 / 1
-  const int tid = threadIdx.x & 127;        // row of the pipeline's tile
+  const int group = threadIdx.x / kPT;      // pipeline 0 / 1
+  const int ptid = threadIdx.x % kPT;       // thread of the pipeline
+  const int tid = ptid & 127;               // row of the pipeline's tile
+  const int half = ptid >> 7;               // 0, or 1 for the second thread of the row (W == 8)
   const int warp = tid >> 5;                // TMEM lane quarter (warp_id % 4 of the real warp)
   uint4 *ax = ax_all + group * kAXVecs;
   uint4 *ax_tail = tail_all + group * kTailVecs;
 
   // ---- one-time setup: weights + biases -> smem, mbarriers, TMEM ----------------------
-  for (int i = threadIdx.x; i < (P.k1pad / 8) * C1; i += G * kRows) w1s[i] = P.w1p[i];
-  for (int i = threadIdx.x; i < (C1 / 8) * C2; i += G * kRows) w2s[i] = P.w2p[i];
-  for (int i = threadIdx.x; i < (C2 / 8) * C3; i += G * kRows) w3s[i] = P.w3p[i];
-  for (int i = threadIdx.x; i < C1; i += G * kRows) s_b1[i] = P.b1[i];
-  for (int i = threadIdx.x; i < C2; i += G * kRows) s_b2[i] = P.b2[i];
-  for (int i = threadIdx.x; i < C3; i += G * kRows) s_b3[i] = P.b3[i];
+  for (int i = threadIdx.x; i < (P.k1pad / 8) * C1; i += G * kPT) w1s[i] = P.w1p[i];
+  for (int i = threadIdx.x; i < (C1 / 8) * C2; i += G * kPT) w2s[i] = P.w2p[i];
+  for (int i = threadIdx.x; i < (C2 / 8) * C3; i += G * kPT) w3s[i] = P.w3p[i];
+  for (int i = threadIdx.x; i < C1; i += G * kPT) s_b1[i] = P.b1[i];
+  for (int i = threadIdx.x; i < C2; i += G * kPT) s_b2[i] = P.b2[i];
+  for (int i = threadIdx.x; i < C3; i += G * kPT) s_b3[i] = P.b3[i];
   if (threadIdx.x == 0) {
     mbar_init(smem_u32(&s_bar[0]), 1);
     mbar_init(smem_u32(&s_bar[1]), 1);
@@ -263,9 +274,11 @@ sa_mlp_max_kernel(const SaParams P) {
       const bool last = kc0 + kKChunk >= k_main;
       // 16-byte-aligned all-feature chunks: 4 chunks (8 independent 16-byte loads) in flight
       // (8 chunks in flight measured 1.8x SLOWER per tile: 10.8k vs 6.2k cycles at SA2)
+      // (with two threads per row the rounds of 4 chunks alternate between them)
       int q = 0;
       if (P.feat_vec4) {
         for (; q + 4 <= nq && kc0 + (q + 4) * 8 <= P.c; q += 4) {
+          if (W == 8 && ((q >> 2) & 1) != half) continue;
           float4 lo[4], hi[4];
 #pragma unroll
           for (int u = 0; u < 4; ++u) {
@@ -279,17 +292,18 @@ sa_mlp_max_kernel(const SaParams P) {
                            pack2(hi[u].x, hi[u].y, P.fp16), pack2(hi[u].z, hi[u].w, P.fp16));
         }
       }
-      for (; q < nq; ++q) gather_q(kc0 + q * 8, &ax[q * kRows + tid]);
+      for (; q < nq; ++q)
+        if (W == 4 || (q & 1) == half) gather_q(kc0 + q * 8, &ax[q * kRows + tid]);
       if (last && P.tail_sep) {
-        gather_q(k_main, &ax_tail[tid]);
-        gather_q(k_main + 8, &ax_tail[kRows + tid]);
+        if (W == 4 || half == 0) gather_q(k_main, &ax_tail[tid]);
+        if (W == 4 || half == 1) gather_q(k_main + 8, &ax_tail[kRows + tid]);
       }
       SA_TRACE(1)
       umma::fence_proxy_async_smem();
       umma::fence_before_sync();
-      group_sync(group);
+      group_sync<W * 32>(group);
       SA_TRACE(2)
-      if (tid == 0) {
+      if (ptid == 0) {
         umma::fence_after_sync();
         for (int ks = 0; ks < kcn / 16; ++ks) {
           const uint64_t ad = umma::smem_desc(ax_addr + (uint32_t)(2 * ks) * kRows * 16, kRows * 16, 128);
@@ -315,12 +329,13 @@ sa_mlp_max_kernel(const SaParams P) {
     }
 
     // ---- epilogue 1 -> X1 ; layer 2 ---------------------------------------------------
-    epilogue_rows<C1>(tmem_d1, warp, tid, s_b1, ax, P.fp16);
+    epilogue_rows<C1>(tmem_d1, warp, tid, s_b1, ax, P.fp16, W == 8 ? half * (C1 / 2) : 0,
+                      W == 8 ? (half + 1) * (C1 / 2) : C1);
     SA_TRACE(4)
     umma::fence_proxy_async_smem();
     umma::fence_before_sync();
-    group_sync(group);
-    if (tid == 0) {
+    group_sync<W * 32>(group);
+    if (ptid == 0) {
       umma::fence_after_sync();
 #pragma unroll
       for (int ks = 0; ks < C1 / 16; ++ks) {
@@ -336,12 +351,13 @@ sa_mlp_max_kernel(const SaParams P) {
 
     SA_TRACE(5)
     // ---- epilogue 2 -> X2 ; layer 3 (transposed: channels on lanes) ---------------------
-    epilogue_rows<C2>(tmem_d2, warp, tid, s_b2, ax, P.fp16);
+    epilogue_rows<C2>(tmem_d2, warp, tid, s_b2, ax, P.fp16, W == 8 ? half * (C2 / 2) : 0,
+                      W == 8 ? (half + 1) * (C2 / 2) : C2);
     SA_TRACE(6)
     umma::fence_proxy_async_smem();
     umma::fence_before_sync();
-    group_sync(group);
-    if (tid == 0) {
+    group_sync<W * 32>(group);
+    if (ptid == 0) {
       umma::fence_after_sync();
 #pragma unroll
       for (int mt = 0; mt < C3 / 128; ++mt) {
@@ -365,8 +381,10 @@ sa_mlp_max_kernel(const SaParams P) {
       const int ch = mt * 128 + tid;
       const float bias = s_b3[ch];
       float run = -INFINITY;
-#pragma unroll
-      for (int c0 = 0; c0 < kRows; c0 += 64) {
+      // (W == 8: each of the row's two threads folds one half of the 128 position columns;
+      //  a group of nsample <= 64 columns never straddles the halves)
+#pragma unroll 1
+      for (int c0 = (W == 8 ? half * 64 : 0); c0 < (W == 8 ? half * 64 + 64 : kRows); c0 += 64) {
         uint32_t va[32], vb[32];
         umma::ld_32x32b_x32(tmem_d3 + mt * 128 + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0, va);
         umma::ld_32x32b_x32(tmem_d3 + mt * 128 + ((uint32_t)(warp * 32) << 16) + (uint32_t)(c0 + 32), vb);
@@ -393,7 +411,7 @@ sa_mlp_max_kernel(const SaParams P) {
     }
     SA_TRACE(8)
     umma::fence_before_sync();
-    group_sync(group);     // TMEM (D3T aliases D1/D2) and the A/X buffer are free again
+    group_sync<W * 32>(group);     // TMEM (D3T aliases D1/D2) and the A/X buffer are free again
     umma::fence_after_sync();
   }
 
@@ -443,7 +461,7 @@ int sa_ctas_per_sm(size_t smem) {
   return max(1, min(per_sm, 512 / kTmemCols));
 }
 
-template <int C1, int C2, int C3, int G>
+template <int C1, int C2, int C3, int G, int W>
 int launch_sa_g(SaParams P, cudaStream_t stream) {
   size_t smem = sa_smem_bytes<C1, C2, C3>(P.k1pad, G);
   // own buffer for a 16-channel K tail when it costs neither the launch nor a resident CTA
@@ -458,7 +476,7 @@ int launch_sa_g(SaParams P, cudaStream_t stream) {
   }
   if (smem > 227 * 1024)
     return set_error(BQA_ERR_UNSUPPORTED, "sa_mlp_max: needs %zu bytes of shared memory", smem);
-  auto kern = sa_mlp_max_kernel<C1, C2, C3, G>;
+  auto kern = sa_mlp_max_kernel<C1, C2, C3, G, W>;
   BQA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int dev = 0, sms = 148;
   BQA_CUDA(cudaGetDevice(&dev));
@@ -469,25 +487,33 @@ int launch_sa_g(SaParams P, cudaStream_t stream) {
   unsigned long long zeros[16] = {0};
   cudaMemcpyToSymbol(g_sa_trace, zeros, sizeof(zeros));
 #endif
-  kern<<<grid, G * kRows, smem, stream>>>(P);
+  kern<<<grid, G * W * 32, smem, stream>>>(P);
 #ifdef BQA_SA_TRACE
   unsigned long long t[16];
   cudaMemcpyFromSymbol(t, g_sa_trace, sizeof(t));
   const double tiles = (double)((P.num_tiles - 0 + grid * G - 1) / (grid * G));
-  fprintf(stderr, "[bqa sa trace] <%d,%d,%d,G=%d> c=%d ns=%d grid=%d tiles/pipeline=%.0f | cycles per tile: idx+xyz %.0f | "
+  fprintf(stderr, "[bqa sa trace] <%d,%d,%d,G=%d,W=%d> c=%d ns=%d grid=%d tiles/pipeline=%.0f | cycles per tile: idx+xyz %.0f | "
           "gather+pack %.0f | sync %.0f | mma1 %.0f | epi1 %.0f | sync+mma2 %.0f | epi2 %.0f | sync+mma3 %.0f | epi3 %.0f | "
-          "tail sync+loop %.0f\n", C1, C2, C3, G, P.c, P.nsample, grid, tiles, t[0] / tiles, t[1] / tiles, t[2] / tiles,
+          "tail sync+loop %.0f\n", C1, C2, C3, G, W, P.c, P.nsample, grid, tiles, t[0] / tiles, t[1] / tiles, t[2] / tiles,
           t[3] / tiles, t[4] / tiles, t[5] / tiles, t[6] / tiles, t[7] / tiles, t[8] / tiles, t[9] / tiles);
 #endif
   count_launch();
   return check_launch("sa_mlp_max_kernel");
 }
 
-// two tile pipelines per CTA when both A/X buffers fit beside the resident weights
+// Two tile pipelines per CTA when both A/X buffers fit beside the resident weights.  Eight warps per
+// pipeline (two threads per row) when only one CTA fits an SM anyway -- then the 512 (or 256)
+// threads still get 128 registers each -- and a group of nsample columns fits one half tile.
+// BQA_SA_WARPS=4 forces the four-warp pipelines (measurement).
 template <int C1, int C2, int C3>
 int launch_sa(const SaParams &P, cudaStream_t stream) {
-  if (sa_smem_bytes<C1, C2, C3>(P.k1pad, 2) <= 227 * 1024) return launch_sa_g<C1, C2, C3, 2>(P, stream);
-  return launch_sa_g<C1, C2, C3, 1>(P, stream);
+  static const int forced = [] { const char *e = getenv("BQA_SA_WARPS"); return e ? atoi(e) : 0; }();
+  const bool two = sa_smem_bytes<C1, C2, C3>(P.k1pad, 2) <= 227 * 1024;
+  const size_t smem = sa_smem_bytes<C1, C2, C3>(P.k1pad, two ? 2 : 1);
+  const int per_sm = two ? sa_ctas_per_sm<C1, C2, C3, 2>(smem) : sa_ctas_per_sm<C1, C2, C3, 1>(smem);
+  const bool wide = forced != 4 && per_sm == 1 && P.nsample <= 64 && C1 % 128 == 0 && C2 % 128 == 0;
+  if (two) return wide ? launch_sa_g<C1, C2, C3, 2, 8>(P, stream) : launch_sa_g<C1, C2, C3, 2, 4>(P, stream);
+  return wide ? launch_sa_g<C1, C2, C3, 1, 8>(P, stream) : launch_sa_g<C1, C2, C3, 1, 4>(P, stream);
 }
 
 }  // namespace
