@@ -30,6 +30,8 @@ _SIGNATURES = {
     "bqa_group_points_grad_workspace_bytes": ([_I, _I, _I], _LL),
     "bqa_group_points_grad_ws": ([_I, _I, _I, _I, _I, _P, _P, _P, _P, _P], _I),
     "bqa_group_concat_point_major": ([_I, _I, _I, _I, _I, _I, _P, _P, _P, _P, _F, _I, _P, _P], _I),
+    "bqa_nms3d": ([_I, _I, _P, _P, ctypes.c_double, _I, _I, _P, _P, _P], _I),
+    "bqa_count_points_in_boxes": ([_I, _I, _I, _P, _P, _P, _P], _I),
     "bqa_nn_distance": ([_I, _I, _I, _P, _P, _I, _F, _P, _P, _P, _P, _P], _I),
     "bqa_bn_relu_max_supported": ([_I], _I),
     "bqa_bn_train_stats": ([_I, _I, _LL, _P, _P, _F, _F, _P, _P, _P, _P, _P], _I),

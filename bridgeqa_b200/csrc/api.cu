@@ -45,6 +45,10 @@ int fps_dispatch(int b, int n, int m, int j_begin, int j_end, const float *xyz, 
                  cudaStream_t stream);
 int nn_distance_dispatch(int b, int n, int m, int mode, float delta, const float *pc1, const float *pc2,
                          float *dist1, long long *idx1, float *dist2, long long *idx2, cudaStream_t stream);
+int nms3d_dispatch(int b, int k, const float *boxes, const int *valid, double thr, int old_type, int same_cls,
+                   int *pick, int *order, cudaStream_t stream);
+int count_in_boxes_dispatch(int b, int n, int k, const float *xyz, const float *lohi, int *counts,
+                            cudaStream_t stream);
 bool bn_relu_max_supported(int ns);
 int bn_stats_dispatch(int b, int c, long long l, const float *y, double *sums, float eps, float momentum,
                       float *mean, float *invstd, float *running_mean, float *running_var,
@@ -418,6 +422,24 @@ int bqa_nn_distance(int b, int n, int m, const float *pc1, const float *pc2, int
   BQA_REQUIRE(n > 0 && m > 0, "%s: both point sets must be non-empty (torch.min over an empty axis raises)", __func__);
   PTR(pc1); PTR(pc2); PTR(dist1); PTR(idx1); PTR(dist2); PTR(idx2);
   return nn_distance_dispatch(b, n, m, mode, delta, pc1, pc2, dist1, idx1, dist2, idx2, (cudaStream_t)stream);
+}
+
+int bqa_nms3d(int b, int k, const float *boxes, const int *valid, double iou_threshold, int old_type,
+              int same_class, int *pick_mask, int *pick_order, void *stream) {
+  NONNEG(b); NONNEG(k);
+  if ((long long)b * k == 0) return BQA_OK;
+  PTR(boxes); PTR(pick_mask);
+  return nms3d_dispatch(b, k, boxes, valid, iou_threshold, old_type != 0, same_class != 0, pick_mask, pick_order,
+                        (cudaStream_t)stream);
+}
+
+int bqa_count_points_in_boxes(int b, int n, int k, const float *xyz, const float *box_lo_hi, int *counts,
+                              void *stream) {
+  NONNEG(b); NONNEG(n); NONNEG(k);
+  if ((long long)b * k == 0) return BQA_OK;
+  PTR(box_lo_hi); PTR(counts);
+  if (n > 0) PTR(xyz);
+  return count_in_boxes_dispatch(b, n, k, xyz, box_lo_hi, counts, (cudaStream_t)stream);
 }
 
 #define ALIGNED16(p) BQA_REQUIRE((reinterpret_cast<uintptr_t>(p) & 15) == 0, "%s: %s must be 16-byte aligned", __func__, #p)

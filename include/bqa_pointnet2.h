@@ -247,6 +247,20 @@ BQA_API int bqa_fp_mlp_forward(int b, int n, int m, int c_known, int c_skip, con
 BQA_API int bqa_nn_distance(int b, int n, int m, const float *pc1, const float *pc2, int mode, float delta,
                             float *dist1, long long *idx1, float *dist2, long long *idx2, void *stream);
 
+/* ---- detection post-processing ------------------------------------------
+ * replaces the host loops of lib/ap_helper.py:86-178 (parse_predictions):
+ *   bqa_count_points_in_boxes: counts (b,k) = points of xyz (b,n,3) inside each axis-aligned box
+ *       box_lo_hi (b,k,6) = {x1,y1,z1,x2,y2,z2}, bounds inclusive -- the `remove_empty_box` test
+ *       (:89-100; ScanNet boxes have one heading bin, i.e. they are axis-aligned);
+ *   bqa_nms3d: greedy 3-D NMS of utils/nms.py:74-152 (nms_3d_faster / _samecls) per scene, in
+ *       double precision like the reference's float64 arrays.  boxes (b,k,8) = {x1,y1,z1,x2,y2,z2,
+ *       score,class}; valid (b,k) or NULL masks boxes out before NMS; pick_mask (b,k) 0/1;
+ *       pick_order (b,k) or NULL lists the picked indices in pick order, -1 padded.  k <= 1024. */
+BQA_API int bqa_nms3d(int b, int k, const float *boxes, const int *valid, double iou_threshold,
+                      int old_type, int same_class, int *pick_mask, int *pick_order, void *stream);
+BQA_API int bqa_count_points_in_boxes(int b, int n, int k, const float *xyz, const float *box_lo_hi,
+                                      int *counts, void *stream);
+
 /* ---- train-mode BatchNorm + ReLU (+ max over nsample) --------------------------------------
  * replaces, in model.train(), the nn.BatchNorm2d (training=True) + shared nn.ReLU that follow
  * every 1x1 conv of a SharedMLP block (lib/pointnet2/pytorch_utils.py:11-36, 73-80) and, for the

@@ -1,0 +1,93 @@
+"""device NMS / point-in-box counts vs a NumPy statement of the same greedy
+rule (utils/nms.py:74-152 semantics: float64 arithmetic, descending score, overlap > threshold
+suppresses) and of the inclusive box test."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from bridgeqa_b200 import postprocess as pp  # noqa: E402
+
+
+def greedy_nms(boxes, thr, old_type=False, same_cls=False):
+    b = boxes.astype(np.float64)
+    vol = (b[:, 3] - b[:, 0]) * (b[:, 4] - b[:, 1]) * (b[:, 5] - b[:, 2])
+    order = sorted(range(len(b)), key=lambda i: (-b[i, 6], i))
+    alive = [True] * len(b)
+    picks = []
+    for pos, i in enumerate(order):
+        if not alive[i]:
+            continue
+        picks.append(i)
+        for j in order[pos + 1:]:
+            if not alive[j]:
+                continue
+            ext = [max(0.0, min(b[i, 3 + a], b[j, 3 + a]) - max(b[i, a], b[j, a])) for a in range(3)]
+            inter = ext[0] * ext[1] * ext[2]
+            o = inter / vol[j] if old_type else inter / (vol[i] + vol[j] - inter)
+            if o > thr and (not same_cls or b[i, 7] == b[j, 7]):
+                alive[j] = False
+    return picks
+
+
+def random_boxes(rng, k, with_cls):
+    c = rng.uniform(-3, 3, size=(k, 3))
+    s = rng.uniform(0.2, 1.5, size=(k, 3))
+    score = rng.permutation(k).astype(np.float64) / k + rng.uniform(0, 1e-4, size=k)
+    cols = [c - s / 2, c + s / 2, score[:, None]]
+    if with_cls:
+        cols.append(rng.randint(0, 4, size=(k, 1)).astype(np.float64))
+    return np.concatenate(cols, 1).astype(np.float32)
+
+
+@pytest.mark.parametrize("k,thr,old,cls", [(256, 0.25, False, False), (256, 0.25, True, False),
+                                           (256, 0.1, False, True), (37, 0.5, False, False),
+                                           (1000, 0.25, False, True), (1, 0.25, False, False)])
+def test_nms3d_matches_greedy_rule(k, thr, old, cls):
+    rng = np.random.RandomState(k + int(thr * 100))
+    boxes = random_boxes(rng, k, cls)
+    want = greedy_nms(boxes, thr, old, cls)
+    fn = pp.nms_3d_faster_samecls if cls else pp.nms_3d_faster
+    got = fn(torch.from_numpy(boxes).cuda(), thr, old)
+    assert got == want
+
+
+def test_nms3d_batch_with_valid_mask():
+    rng = np.random.RandomState(3)
+    boxes = np.stack([random_boxes(rng, 200, False) for _ in range(3)])
+    valid = rng.rand(3, 200) > 0.3
+    pick, order = pp.nms_3d_batch(torch.from_numpy(boxes).cuda(), 0.25, valid=torch.from_numpy(valid).cuda())
+    for s in range(3):
+        keep = np.where(valid[s])[0]
+        want = [int(keep[i]) for i in greedy_nms(boxes[s][keep], 0.25)]
+        got = order[s][order[s] >= 0].tolist()
+        assert got == want
+        assert sorted(np.where(pick[s].cpu().numpy())[0].tolist()) == sorted(want)
+
+
+def test_count_points_in_boxes_and_prediction_mask():
+    rng = np.random.RandomState(4)
+    xyz = rng.uniform(-2, 2, size=(2, 5000, 3)).astype(np.float32)
+    c = rng.uniform(-2, 2, size=(2, 64, 3)).astype(np.float32)
+    s = rng.uniform(0.05, 1.0, size=(2, 64, 3)).astype(np.float32)
+    lo, hi = c - s / 2, c + s / 2
+    lo[0, 0] = xyz[0, 10]                  # a point exactly on the lower bound counts
+    hi[0, 0] = lo[0, 0] + np.float32(0.5)
+    want = ((xyz[:, None] >= lo[:, :, None]) & (xyz[:, None] <= hi[:, :, None])).all(-1).sum(-1)
+    got = pp.count_points_in_boxes(torch.from_numpy(xyz).cuda(),
+                                   torch.from_numpy(np.concatenate([lo, hi], -1)).cuda())
+    np.testing.assert_array_equal(got.cpu().numpy(), want)
+    # prediction_mask == counts >= 5 filter + NMS on softmax(objectness)[..., 1]
+    corners = np.stack([np.stack([np.where((np.arange(8)[:, None] >> np.arange(3)[None]) & 1, hi[b_, j], lo[b_, j])
+                                  for j in range(64)]) for b_ in range(2)]).astype(np.float32)
+    logits = rng.normal(size=(2, 64, 2)).astype(np.float32)
+    dd = {"bbox_corner": torch.from_numpy(corners).cuda(), "objectness_scores": torch.from_numpy(logits).cuda(),
+          "sem_cls_scores": torch.zeros(2, 64, 18).cuda(), "point_clouds": torch.from_numpy(xyz).cuda()}
+    mask = pp.prediction_mask(dd, nms_iou=0.25).cpu().numpy()
+    prob = torch.softmax(torch.from_numpy(logits), -1)[..., 1].numpy()
+    for b_ in range(2):
+        keep = np.where(want[b_] >= 5)[0]
+        bx = np.concatenate([lo[b_], hi[b_], prob[b_][:, None]], 1)[keep]
+        picks = sorted(int(keep[i]) for i in greedy_nms(bx, 0.25))
+        assert sorted(np.where(mask[b_])[0].tolist()) == picks
