@@ -52,8 +52,10 @@ def test_nn_distance_matches_reference_expression(b, n, m, kw):
     w2 = torch.randn_like(got[2])
     ((got[0] * w1).sum() + (got[2] * w2).sum()).backward()
     ((want[0] * w1).sum() + (want[2] * w2).sum()).backward()
-    torch.testing.assert_close(a1.grad, r1.grad, rtol=1e-5, atol=1e-6)
-    torch.testing.assert_close(a2.grad, r2.grad, rtol=1e-5, atol=1e-6)
+    # gradients are sums of up to n fp32 terms per point, accumulated in a different (atomic,
+    # nondeterministic) order than torch's scatter: the 1e-4 bar of every scatter-add on this path
+    torch.testing.assert_close(a1.grad, r1.grad, rtol=1e-4, atol=1e-5)
+    torch.testing.assert_close(a2.grad, r2.grad, rtol=1e-4, atol=1e-5)
 
 
 def test_nn_distance_errors():
