@@ -352,6 +352,9 @@ def main():
     ap.add_argument("--train-batch", type=int, default=16, help="scenes per GPU in --mode train")
     ap.add_argument("--torch-bn", action="store_true", help="--mode train: torch BatchNorm/ReLU/max_pool modules "
                     "instead of the sm_100a streaming kernels (the reference's module structure)")
+    ap.add_argument("--in-flight", type=int, default=3,
+                    help="batches in flight (graphs.InFlight): consecutive steps are issued on a ring of this many "
+                         "streams so the next batch's sampling chain runs under this batch's SA/FP kernels; 1 = serial")
     ap.add_argument("--precision", default="fp16", choices=["fp16", "bf16"],
                     help="operand format of the fused tensor-core kernels (fp32 accumulate)")
     args = ap.parse_args()
@@ -406,7 +409,12 @@ def main():
     dev_inputs = [h.to(device) for h in host_pinned]
     flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=device)
 
-    def step(i):
+    depth = max(1, min(args.in_flight, ROT))
+    queue = net.in_flight(depth)       # public API (graphs.InFlight): `depth` forwards in flight
+
+    def step(i, q=None):
+        if q is not None:              # step i and step i + ROT share a graph: ROT % depth == 0 keeps them on one stream
+            return q.submit({"point_clouds": dev_inputs[i % ROT]})
         with torch.no_grad():
             return net({"point_clouds": dev_inputs[i % ROT]})[out_key]
 
@@ -422,6 +430,9 @@ def main():
     rank_sm_clock(local_rank)          # NVML initialised here, not inside the timed region
     for i in range(max(args.warmup, ROT if not args.no_graph else 0)):   # every input buffer's graph exists
         step(i)
+    for i in range(max(args.warmup, ROT) if depth > 1 else 0):
+        step(i, queue)
+    queue.drain()
     barrier()
 
     # ---- timed region: exactly K steps, device-timed ----
@@ -432,15 +443,28 @@ def main():
     t_host0 = time.perf_counter()
     my_sm_mhz = -1.0
     for i in range(args.steps):
-        step(i)
+        step(i, queue if depth > 1 else None)
         if i == args.steps // 2:
             my_sm_mhz = rank_sm_clock(local_rank)     # this rank's GPU, mid-run (NVML, host side only)
     host_issue_ms = (time.perf_counter() - t_host0) * 1e3 / args.steps
+    queue.drain()                      # the timing stream waits for every forward in flight
     ev1.record()
     barrier()
     clocks.mark_end()
     elapsed_ms = ev0.elapsed_time(ev1)
     clk = clocks.stop() if rank == 0 else None
+
+    # ---- the same K steps one batch at a time (latency of a batch; not the headline) ----
+    serial_ms = elapsed_ms
+    if depth > 1:
+        s0 = torch.cuda.Event(enable_timing=True)
+        s1 = torch.cuda.Event(enable_timing=True)
+        s0.record()
+        for i in range(args.steps):
+            step(i)
+        s1.record()
+        barrier()
+        serial_ms = s0.elapsed_time(s1)
 
     # ---- per-kernel pass: the same K steps again with a CUDA-event pair around every C-ABI
     # call (on the stream it is launched on).  Kept out of the pass above because ~50 extra
@@ -478,53 +502,43 @@ def main():
     h2d_bytes = host_pinned[0].numel() * 4
     d2h_bytes = sum(t.numel() * t.element_size() for t in out_host.values())
 
-    # double-buffered: the H2D copy of step i+1 and the D2H read of step i-1 run on their own
-    # streams underneath the forward of step i; every copy is inside the timed region
+    # pipelined: NB = depth + 1 device input buffers, each with its own graph and static outputs
+    # (bind_inputs).  The H2D copy of step i runs on copy_in as soon as the forward that last read
+    # its buffer (step i - NB) is done; the forward goes through the in-flight queue; the D2H read
+    # of its results runs on copy_out straight out of the graph's output buffers, and the next
+    # forward on that buffer (step i + NB) waits for the read.  Every copy is inside the timed region.
     copy_in, copy_out = torch.cuda.Stream(device), torch.cuda.Stream(device)
     main = torch.cuda.current_stream(device)
-    dev_buf = [torch.empty_like(dev_inputs[0]) for _ in range(2)]
-    in_ready = [torch.cuda.Event() for _ in range(2)]
-    buf_free = [torch.cuda.Event() for _ in range(2)]
-    out_done = torch.cuda.Event()
-
-    # graph replay returns static output buffers that the next replay overwrites: a step's
-    # results are first copied (device to device, on the main stream) into one of two staging
-    # sets and read back to the host from there
-    stage = [{k_: torch.empty(t_.shape, dtype=t_.dtype, device=device) for k_, t_ in out_host.items()}
-             for _ in range(2)]
-    stage_free = [torch.cuda.Event() for _ in range(2)]
+    NB = depth + 1
+    dev_buf = [torch.empty_like(dev_inputs[0]) for _ in range(NB)]
 
     def e2e_run(k):
-        with torch.no_grad():
+        fwd_done = [None] * NB
+        read_done = [None] * NB
+        start = torch.cuda.Event()
+        start.record(main)
+        copy_in.wait_event(start)
+        for i in range(k):
+            j = i % NB
             with torch.cuda.stream(copy_in):
-                dev_buf[0].copy_(host_pinned[0], non_blocking=True)
-                in_ready[0].record(copy_in)
-            for i in range(k):
-                cur, nxt = i & 1, (i + 1) & 1
-                if i + 1 < k:
-                    with torch.cuda.stream(copy_in):
-                        if i >= 1:
-                            copy_in.wait_event(buf_free[nxt])      # forward i-1 no longer reads it
-                        dev_buf[nxt].copy_(host_pinned[(i + 1) % ROT], non_blocking=True)
-                        in_ready[nxt].record(copy_in)
-                main.wait_event(in_ready[cur])
-                dd = net({"point_clouds": dev_buf[cur]})
-                buf_free[cur].record(main)
-                if i >= 2:
-                    main.wait_event(stage_free[cur])               # read-back of step i-2 is done
-                for k_ in out_host:
-                    stage[cur][k_].copy_(dd[k_])
-                fwd_done = torch.cuda.Event()
-                fwd_done.record(main)
-                with torch.cuda.stream(copy_out):
-                    copy_out.wait_event(fwd_done)
-                    for k_, t_ in out_host.items():
-                        t_.copy_(stage[cur][k_], non_blocking=True)
-                    stage_free[cur].record(copy_out)
-                    out_done.record(copy_out)
-            main.wait_event(out_done)
+                if fwd_done[j] is not None:
+                    copy_in.wait_event(fwd_done[j])                # forward i-NB no longer reads the buffer
+                dev_buf[j].copy_(host_pinned[i % ROT], non_blocking=True)
+                ready = torch.cuda.Event()
+                ready.record(copy_in)
+            ticket = queue.submit({"point_clouds": dev_buf[j]},
+                                  after=[ready] + ([read_done[j]] if read_done[j] is not None else []))
+            fwd_done[j] = ticket.done
+            with torch.cuda.stream(copy_out):
+                dd = ticket.wait(copy_out)
+                for k_, t_ in out_host.items():
+                    t_.copy_(dd[k_], non_blocking=True)
+                read_done[j] = torch.cuda.Event()
+                read_done[j].record(copy_out)
+        main.wait_stream(copy_out)
+        main.wait_stream(copy_in)
 
-    e2e_run(3)
+    e2e_run(2 * NB)
     barrier()
     e0 = torch.cuda.Event(enable_timing=True)
     e1 = torch.cuda.Event(enable_timing=True)
@@ -535,7 +549,7 @@ def main():
     e2e_ms = e0.elapsed_time(e1)
 
     # max over ranks
-    t = torch.tensor([elapsed_ms, e2e_ms, my_sm_mhz], dtype=torch.float64, device=device)
+    t = torch.tensor([elapsed_ms, e2e_ms, my_sm_mhz, serial_ms], dtype=torch.float64, device=device)
     by_rank = [elapsed_ms / args.steps]
     mhz_by_rank = [my_sm_mhz]
     if world > 1:
@@ -544,7 +558,7 @@ def main():
         by_rank = [float(x[0]) / args.steps for x in every]       # device time of each rank's K steps
         mhz_by_rank = [float(x[2]) for x in every]
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    elapsed_ms, e2e_ms = float(t[0]), float(t[1])
+    elapsed_ms, e2e_ms, serial_ms = float(t[0]), float(t[1]), float(t[3])
 
     if rank == 0:
         peaks = measured_peaks()
@@ -610,7 +624,14 @@ def main():
                        "l2": "inputs rotate over %d resident batches (%.0f MB) + >1 GB intermediate traffic per step"
                              % (ROT, ROT * h2d_bytes / 1e6),
                        "fused": any(r["bound"] == "tensor" for r in kernels), "torch_tf32": bool(args.tf32),
-                       "cuda_graph": not args.no_graph},
+                       "cuda_graph": not args.no_graph,
+                       "in_flight": depth,
+                       "in_flight_note": "consecutive steps are issued on a ring of %d streams (graphs.InFlight): each step "
+                                         "is still one forward over one batch of 16 scenes; the next batch's sampling chain "
+                                         "(96 SMs, latency-bound) runs under this batch's SA/FP kernels; "
+                                         "serial.ms_per_step is one batch at a time" % depth},
+            "serial": {"ms_per_step": serial_ms / args.steps, "value": scenes / (serial_ms / 1e3), "unit": UNIT,
+                       "note": "same K steps with one batch in flight = latency of a batch"},
             "e2e": {"value": scenes / (e2e_ms / 1e3), "unit": UNIT, "ms_per_step": e2e_ms / args.steps,
                     "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes},
             "ms_per_step_by_rank": [round(v, 4) for v in by_rank],

@@ -46,7 +46,7 @@ namespace {
 constexpr int kT = 512;
 constexpr int kNW = kT / 32;
 constexpr int kMaxCluster = 16;
-constexpr int kMaxP = 18;
+constexpr int kMaxP = 20;
 constexpr unsigned kFull = 0xffffffffu;
 
 struct __align__(16) Cand {      // 32-byte slot, two 16-byte halves (st.async v4 + b32)
@@ -299,7 +299,7 @@ int fps_sorted_dispatch(int b, int n, int m, const float *xyz, const void *grid,
   int rc = BQA_ERR_UNSUPPORTED;
 #define BQA_SORTED_CASE(PP) if (per <= PP) { rc = launch_sorted<PP>(b, n, m, cs, sorted, xyz, idxs, new_xyz, stream); } else
   BQA_SORTED_CASE(1) BQA_SORTED_CASE(2) BQA_SORTED_CASE(4) BQA_SORTED_CASE(6) BQA_SORTED_CASE(8)
-  BQA_SORTED_CASE(10) BQA_SORTED_CASE(12) BQA_SORTED_CASE(14) BQA_SORTED_CASE(16) BQA_SORTED_CASE(18)
+  BQA_SORTED_CASE(10) BQA_SORTED_CASE(12) BQA_SORTED_CASE(14) BQA_SORTED_CASE(16) BQA_SORTED_CASE(18) BQA_SORTED_CASE(20)
   { rc = set_error(BQA_ERR_UNSUPPORTED, "fps (sorted): %d points per thread", per); }
 #undef BQA_SORTED_CASE
   return rc;

@@ -117,6 +117,12 @@ class Pointnet2Backbone(nn.Module):
         self._graphed = self._graph_runner if on else None
         return self
 
+    def in_flight(self, depth=2):
+        """Queue that keeps `depth` inference forwards in flight on their own streams, so that
+        the next batch's sampling chain runs under this batch's SA/FP kernels (graphs.InFlight)."""
+        from . import graphs
+        return graphs.InFlight(self, depth)
+
     def forward(self, data_dict):
         g = getattr(self, "_graphed", None)
         if g is not None and g.applicable(data_dict):
@@ -367,6 +373,12 @@ class VoteNetDetector(nn.Module):
             self._graph_runner = graphs.GraphedForward(self, self._forward_impl, bind_inputs)
         self._graphed = self._graph_runner if on else None
         return self
+
+    def in_flight(self, depth=2):
+        """Queue that keeps `depth` inference forwards in flight on their own streams, so that
+        the next batch's sampling chain runs under this batch's SA/FP kernels (graphs.InFlight)."""
+        from . import graphs
+        return graphs.InFlight(self, depth)
 
     def forward(self, data_dict):
         g = getattr(self, "_graphed", None)

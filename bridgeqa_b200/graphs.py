@@ -79,3 +79,85 @@ class GraphedForward(object):
                 out = self.impl({"point_clouds": inp})
         out = {k: v for k, v in out.items() if k != "point_clouds"}
         return {"graph": graph, "inp": inp, "out": out, "sig": sig}
+
+
+class Ticket(object):
+    """One submitted forward: `out` (the module's data_dict) is valid once `done` has fired."""
+
+    def __init__(self, out, done, stream, static):
+        self.out, self.done, self.stream, self.static = out, done, stream, static
+
+    def wait(self, stream=None):
+        """Make `stream` (default: the current one) wait for this forward; returns the data_dict."""
+        dev = self.stream.device
+        stream = torch.cuda.current_stream(dev) if stream is None else stream
+        stream.wait_event(self.done)
+        if not self.static:
+            # eager outputs belong to the caching allocator on the forward's stream
+            for t in self.out.values():
+                if torch.is_tensor(t) and t.is_cuda:
+                    t.record_stream(stream)
+        return self.out
+
+
+class InFlight(object):
+    """Keeps `depth` inference forwards of a module in flight, each on its own stream.
+
+    The sampling chain of a 40k-point batch holds 96 of the 148 SMs for ~60 % of its forward and
+    is pure SM-to-SM latency (2047 dependent argmax steps); the SA/FP kernels that follow are
+    short.  Consecutive batches are independent, so the next batch's chain is issued on another
+    stream and runs underneath the current batch's SA/FP kernels (measured on B200, graphed
+    backbone, 16 x 40k: 2.03 ms/step serial, 1.53 with two batches in flight, 1.46 with three;
+    outputs bit-identical).
+
+        q = net.in_flight(depth=3)
+        t = q.submit({"point_clouds": pc})        # returns at once
+        ...
+        out = t.wait()                            # current stream now waits for that forward
+
+    With enable_cuda_graph(bind_inputs=True) every input buffer owns a graph and its static
+    outputs, so forwards of different buffers overlap freely; a buffer (and its outputs) must not
+    be reused before the ticket of its previous forward has been waited for."""
+
+    def __init__(self, module, depth=2):
+        if depth < 1:
+            raise ValueError("in_flight depth must be >= 1")
+        self.module, self.depth = module, int(depth)
+        self._streams = {}
+        self.submitted = 0
+
+    def streams(self, device):
+        key = torch.device(device).index
+        if key not in self._streams:
+            self._streams[key] = [torch.cuda.Stream(device) for _ in range(self.depth)]
+        return self._streams[key]
+
+    def submit(self, data_dict, after=None):
+        """Issue module(data_dict) on the next stream of the ring.  `after`: event or list of
+        events the forward has to wait for (default: everything queued on the current stream)."""
+        pc = data_dict["point_clouds"]
+        if not (torch.is_tensor(pc) and pc.is_cuda):
+            raise RuntimeError("in-flight forwards need a CUDA point cloud (no CPU path)")
+        s = self.streams(pc.device)[self.submitted % self.depth]
+        self.submitted += 1
+        if after is None:
+            after = torch.cuda.Event()
+            after.record(torch.cuda.current_stream(pc.device))
+        for ev in (after if isinstance(after, (list, tuple)) else (after,)):
+            s.wait_event(ev)
+        g = getattr(self.module, "_graphed", None)
+        with torch.cuda.stream(s), torch.no_grad():
+            static = g is not None and g.applicable(data_dict)
+            if not static:
+                pc.record_stream(s)
+            out = self.module(data_dict)
+            done = torch.cuda.Event()
+            done.record(s)
+        return Ticket(out, done, s, static)
+
+    def drain(self, stream=None):
+        """`stream` (default: current) waits for every forward submitted so far."""
+        for dev, ring in self._streams.items():
+            cur = torch.cuda.current_stream(ring[0].device) if stream is None else stream
+            for s in ring:
+                cur.wait_stream(s)

@@ -365,6 +365,33 @@ def test_cuda_graph_replay_equals_eager(which, c, _restore_fused):
         assert not torch.equal(out[keys[0]], eager[0][keys[0]])
 
 
+@pytest.mark.parametrize("graph", [False, True])
+@pytest.mark.parametrize("depth", [1, 2, 3])
+def test_in_flight_forwards_equal_serial(graph, depth, _restore_fused):
+    """graphs.InFlight: forwards issued on a ring of streams (the next batch's sampling chain
+    under this batch's SA/FP kernels) return exactly what one-at-a-time forwards return."""
+    net = synthetic.fill_state_dict(detector.Pointnet2Backbone(input_feature_dim=4), seed=0).cuda().eval()
+    keys = ["fp2_features", "fp2_inds", "sa1_inds", "sa4_features"]
+    pcs = [synthetic.make_batch(2, 20000, 4, first_scene=5 * i).cuda() for i in range(4)]
+    with torch.no_grad():
+        want = [{k: net({"point_clouds": p})[k].clone() for k in keys} for p in pcs]
+    if graph:
+        net.enable_cuda_graph(True, bind_inputs=True)
+    q = net.in_flight(depth)
+    for rep in range(2):
+        tickets = [q.submit({"point_clouds": p}) for p in pcs]
+        for t, w in zip(tickets, want):
+            out = t.wait()
+            for k in keys:
+                assert torch.equal(out[k], w[k]), (graph, depth, rep, k)
+    q.drain()
+    torch.cuda.synchronize()
+    assert q.submitted == 8
+    with pytest.raises(RuntimeError):
+        q.submit({"point_clouds": pcs[0].cpu()})
+    net.enable_cuda_graph(False)
+
+
 @pytest.mark.parametrize("B,cin,spec,npoint,ns", [
     (2, 6, [16, 16], 64, 16), (3, 10, [64, 64, 128], 128, 32), (2, 12, [128], 33, 64),
     (2, 5, [8, 8], 10, 4), (2, 7, [16, 24], 20, 6),          # ns = 6: pooled falls back to max_pool2d
