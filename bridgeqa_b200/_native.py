@@ -41,6 +41,7 @@ _SIGNATURES = {
     "bqa_bn_relu_max_backward": ([_I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P], _I),
     "bqa_fps_grid_supported": ([_I, _I], _I),
     "bqa_furthest_point_sampling_grid": ([_I, _I, _I, _P, _P, _P, _P, _P], _I),
+    "bqa_furthest_point_sampling_grid_lean": ([_I, _I, _I, _P, _P, _P, _P, _P], _I),
     "bqa_fps_prefix_check": ([_I, _I, _I, _P, _P, _P, _P], _I),
     "bqa_furthest_point_sampling_cond": ([_I, _I, _I, _P, _P, _P, _P, _P, _P], _I),
     "bqa_gather_points": ([_I, _I, _I, _I, _P, _P, _P, _P], _I),

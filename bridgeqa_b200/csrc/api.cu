@@ -67,7 +67,7 @@ int bn_relu_max_backward_dispatch(int b, int c, long long np, int ns, const floa
                                   cudaStream_t stream);
 bool fps_sorted_supported(int n, int m);
 int fps_sorted_dispatch(int b, int n, int m, const float *xyz, const void *grid, int *idxs,
-                        float *new_xyz, cudaStream_t stream);
+                        float *new_xyz, int lean, cudaStream_t stream);
 bool fps_prefix_check_supported(int n, int m);
 int fps_prefix_check_dispatch(int b, int n, int m, const float *xyz, float *v_scratch, int *run_flags,
                               cudaStream_t stream);
@@ -151,7 +151,17 @@ int bqa_furthest_point_sampling_grid(int b, int n, int m, const float *xyz, cons
   BQA_REQUIRE(fps_sorted_supported(n, m), "%s: n=%d is outside what the sorted kernel takes "
               "(see bqa_fps_grid_supported)", __func__, n);
   PTR(xyz); PTR(grid); PTR(idxs);
-  return fps_sorted_dispatch(b, n, m, xyz, grid, idxs, new_xyz, (cudaStream_t)stream);
+  return fps_sorted_dispatch(b, n, m, xyz, grid, idxs, new_xyz, 0, (cudaStream_t)stream);
+}
+
+int bqa_furthest_point_sampling_grid_lean(int b, int n, int m, const float *xyz, const void *grid, int *idxs,
+                                          float *new_xyz, void *stream) {
+  NONNEG(b); NONNEG(n); NONNEG(m);
+  if (b == 0 || m == 0) return BQA_OK;
+  BQA_REQUIRE(fps_sorted_supported(n, m), "%s: n=%d is outside what the sorted kernel takes "
+              "(see bqa_fps_grid_supported)", __func__, n);
+  PTR(xyz); PTR(grid); PTR(idxs);
+  return fps_sorted_dispatch(b, n, m, xyz, grid, idxs, new_xyz, 1, (cudaStream_t)stream);
 }
 
 int bqa_fps_prefix_check(int b, int n, int m, const float *xyz, float *v_scratch, int *run_flags,

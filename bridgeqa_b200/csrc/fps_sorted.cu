@@ -71,15 +71,25 @@ __device__ __forceinline__ uint32_t index_of(uint32_t nk) {
 __device__ unsigned long long g_active_warp_iters;
 #endif
 
-template <int P>
-__global__ void __launch_bounds__(kT, 1)
+// kLean = false: coordinates, running min-distances and tie keys in registers (125 registers x 512
+// threads: the CTA owns its SM), shared memory only holds a copy for the winner's lookup -- the
+// lowest latency per iteration.
+// kLean = true (the throughput variant, T = 1024): only the running min-distances stay in
+// registers; coordinates and tie keys are read from the shared-memory copy {x, y, z, key} by the
+// few warps whose box the new sample can reach.  A 40k-point scene then fits THREE SMs (14336
+// points x 16 bytes = 224 KB each) instead of six, at ~15 % more latency per iteration: with
+// several batches in flight (graphs.InFlight) the chain is not the bottleneck, SM-time is.
+template <int P, int T, bool kLean>
+__global__ void __launch_bounds__(T, 1)
 fps_sorted_kernel(int n, int m, int cs, const float4 *__restrict__ sorted_all,
                   const float *__restrict__ xyz_all, int *__restrict__ idx_all,
                   float *__restrict__ new_xyz_all) {
+  constexpr int kT = T, kNW = T / 32;
+  constexpr int PR = kLean ? 1 : P;      // register copies of coordinates / keys (unused when lean)
   __shared__ Cand recv[2][kMaxCluster];
   __shared__ Cand part[kNW];
   __shared__ __align__(8) uint64_t bars[2];
-  extern __shared__ float4 pts[];        // [P][kT] copy of the coordinates: the winner's lookup by slot
+  extern __shared__ float4 pts[];        // [P][kT] coordinates (+ tie key in .w when lean): the winner's lookup by slot
 
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const uint32_t rank = cs > 1 ? cluster_ctarank() : 0u;
@@ -92,8 +102,8 @@ fps_sorted_kernel(int n, int m, int cs, const float4 *__restrict__ sorted_all,
   // run of 32*P consecutive sorted points per warp; runs dealt round-robin to the CTAs
   const int run = wid * cs + (int)rank;
   const int base = run * (32 * P);
-  float px[P], py[P], pz[P], td[P];
-  uint32_t nkey[P];
+  float px[PR], py[PR], pz[PR], td[P];
+  uint32_t nkey[PR];
   float lox = INFINITY, loy = INFINITY, loz = INFINITY, hix = -INFINITY, hiy = -INFINITY, hiz = -INFINITY;
 #pragma unroll
   for (int p = 0; p < P; ++p) {
@@ -110,8 +120,9 @@ fps_sorted_kernel(int n, int m, int cs, const float4 *__restrict__ sorted_all,
       loy = fminf(loy, y); hiy = fmaxf(hiy, y);
       loz = fminf(loz, z); hiz = fmaxf(hiz, z);
     }
-    px[p] = x; py[p] = y; pz[p] = z; td[p] = t; nkey[p] = nk;
-    pts[p * kT + tid] = make_float4(x, y, z, 0.f);
+    td[p] = t;
+    if constexpr (!kLean) { px[p] = x; py[p] = y; pz[p] = z; nkey[p] = nk; }
+    pts[p * kT + tid] = make_float4(x, y, z, __uint_as_float(nk));
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
@@ -162,7 +173,15 @@ fps_sorted_kernel(int n, int m, int cs, const float4 *__restrict__ sorted_all,
       float best = -INFINITY;
 #pragma unroll
       for (int p = 0; p < P; ++p) {
-        const float dx = px[p] - x1, dy = py[p] - y1, dz = pz[p] - z1;
+        float qx, qy, qz;
+        if constexpr (kLean) {
+          // at most 6 shared-memory loads in flight: more would spill, and with 221 KB of shared
+          // memory the L1 that local memory lives in is a few KB (a spill costs an L2 round trip)
+          if (p % 6 == 0 && p) asm volatile("" ::: "memory");
+          const float4 v = pts[p * kT + tid]; qx = v.x; qy = v.y; qz = v.z;
+        }
+        else { qx = px[p]; qy = py[p]; qz = pz[p]; }
+        const float dx = qx - x1, dy = qy - y1, dz = qz - z1;
         const float d = __fmaf_rn(dz, dz, __fmaf_rn(dx, dx, __fmul_rn(dy, dy)));
         const float d2 = fminf(d, td[p]);
         td[p] = d2;
@@ -175,7 +194,10 @@ fps_sorted_kernel(int n, int m, int cs, const float4 *__restrict__ sorted_all,
         const float wf = __uint_as_float(wvb - 1u);
         uint32_t cand = 0u;
 #pragma unroll
-        for (int p = 0; p < P; ++p) cand = max(cand, td[p] == wf ? nkey[p] : 0u);
+        for (int p = 0; p < P; ++p) {
+          if constexpr (kLean) { if (td[p] == wf) cand = max(cand, __float_as_uint(pts[p * kT + tid].w)); }
+          else cand = max(cand, td[p] == wf ? nkey[p] : 0u);
+        }
         const uint32_t wnk = __reduce_max_sync(kFull, cand);
         if (cand == wnk) {                                 // exactly one lane (keys are distinct, non-zero)
           const float4 w = pts[(wnk & 31u) * kT + tid];    // own slot: no barrier needed
@@ -195,7 +217,7 @@ fps_sorted_kernel(int n, int m, int cs, const float4 *__restrict__ sorted_all,
       uint2 c = lane < kNW ? *reinterpret_cast<const uint2 *>(&part[lane]) : make_uint2(0u, 0u);
       const uint32_t mv = __reduce_max_sync(kFull, c.x);
       win_nk = __reduce_max_sync(kFull, c.x == mv ? c.y : 0u);
-      const Cand *w = &part[win_nk & 15u];
+      const Cand *w = &part[win_nk & 31u];
       x1 = w->x; y1 = w->y; z1 = w->z;
       __syncthreads();             // part[] is rewritten in the next iteration
     } else {
@@ -205,7 +227,7 @@ fps_sorted_kernel(int n, int m, int cs, const float4 *__restrict__ sorted_all,
         uint2 c = lane < kNW ? *reinterpret_cast<const uint2 *>(&part[lane]) : make_uint2(0u, 0u);
         const uint32_t mv = __reduce_max_sync(kFull, c.x);
         const uint32_t mk = __reduce_max_sync(kFull, c.x == mv ? c.y : 0u);
-        const Cand *w = &part[mk & 15u];
+        const Cand *w = &part[mk & 31u];
         const float wx = w->x, wy = w->y, wz = w->z;
         const uint32_t slot = smem_u32(&recv[jj & 1][rank]);
         if (lane == 0) mbar_arrive_expect_tx(bar, 20u * cs);
@@ -234,17 +256,19 @@ fps_sorted_kernel(int n, int m, int cs, const float4 *__restrict__ sorted_all,
   if (cs > 1) cluster_sync_all();  // nobody exits while a peer may still write into it
 }
 
-template <int P>
+template <int P, int T = kT, bool kLean = false>
 int launch_sorted(int b, int n, int m, int cs, const float4 *sorted, const float *xyz, int *idxs,
                   float *new_xyz, cudaStream_t stream) {
+  constexpr int kT = T, kNW = T / 32;
+  auto *kernel = fps_sorted_kernel<P, T, kLean>;
   if (cs > 8)
-    BQA_CUDA(cudaFuncSetAttribute(fps_sorted_kernel<P>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+    BQA_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
   cudaLaunchConfig_t cfg = cudaLaunchConfig_t{};
   cudaLaunchAttribute attr[1];
   cfg.gridDim = dim3((unsigned)(b * cs));
   cfg.blockDim = dim3(kT);
   cfg.dynamicSmemBytes = sizeof(float4) * P * kT;
-  BQA_CUDA(cudaFuncSetAttribute(fps_sorted_kernel<P>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+  BQA_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 (int)cfg.dynamicSmemBytes));
   cfg.stream = stream;
   attr[0].id = cudaLaunchAttributeClusterDimension;
@@ -257,7 +281,7 @@ int launch_sorted(int b, int n, int m, int cs, const float4 *sorted, const float
   unsigned long long zero = 0;
   cudaMemcpyToSymbol(g_active_warp_iters, &zero, sizeof(zero));
 #endif
-  BQA_CUDA(cudaLaunchKernelEx(&cfg, fps_sorted_kernel<P>, n, m, cs, sorted, xyz, idxs, new_xyz));
+  BQA_CUDA(cudaLaunchKernelEx(&cfg, kernel, n, m, cs, sorted, xyz, idxs, new_xyz));
 #ifdef BQA_FPS_STATS
   unsigned long long act = 0;
   cudaMemcpyFromSymbol(&act, g_active_warp_iters, sizeof(act));
@@ -265,6 +289,7 @@ int launch_sorted(int b, int n, int m, int cs, const float4 *sorted, const float
           b, n, m, cs, P, 100.0 * act / ((double)b * cs * kNW * (m - 1)), (double)act / ((double)b * (m - 1)), cs * kNW);
 #endif
   count_launch();
+  (void)kNW;
   return check_launch("fps_sorted_kernel");
 }
 
@@ -276,10 +301,27 @@ bool fps_sorted_supported(int n, int m) {
   return n >= 512 && m >= 1 && (long long)n <= 16ll * kT * kMaxP;
 }
 
+// throughput variant: scenes of up to 8 x 14336 points (a portable cluster of lean CTAs)
+constexpr int kLeanT = 768, kLeanMaxP = 18;
+bool fps_lean_supported(int n, int m) {
+  return n >= 512 && m >= 1 && (long long)n <= 8ll * kLeanT * kLeanMaxP;
+}
+
 int fps_sorted_dispatch(int b, int n, int m, const float *xyz, const void *grid, int *idxs,
-                        float *new_xyz, cudaStream_t stream) {
+                        float *new_xyz, int lean, cudaStream_t stream) {
   if (!fps_sorted_supported(n, m))
     return set_error(BQA_ERR_UNSUPPORTED, "fps (sorted): n=%d not supported", n);
+  static const int env_lean = [] { const char *e = getenv("BQA_FPS_LEAN"); return e ? atoi(e) : -1; }();
+  if (env_lean >= 0) lean = env_lean;                    // developer override
+  if (lean && fps_lean_supported(n, m)) {
+    // fewest CTAs whose shared memory holds the scene; the tail of the last run is padding
+    const int cs = ceil_div(n, kLeanT * kLeanMaxP);
+    const int per = ceil_div(n, cs * kLeanT);
+    const float4 *sorted = ball_query_grid_sorted(grid, b, n);
+#define BQA_LEAN_CASE(PP) if (per <= PP) return launch_sorted<PP, kLeanT, true>(b, n, m, cs, sorted, xyz, idxs, new_xyz, stream);
+    BQA_LEAN_CASE(3) BQA_LEAN_CASE(6) BQA_LEAN_CASE(10) BQA_LEAN_CASE(14) BQA_LEAN_CASE(18)
+#undef BQA_LEAN_CASE
+  }
   // cluster size: same trade-off as fps.cu's plan (co-resident clusters on B200: 22 of 6 CTAs,
   // 33 of 4, 15 of 8), but pruned iterations cost little per point, so fewer, fuller CTAs
   static const int forced = [] { const char *e = getenv("BQA_FPS_SORTED_CS"); return e ? atoi(e) : 0; }();

@@ -117,11 +117,11 @@ class Pointnet2Backbone(nn.Module):
         self._graphed = self._graph_runner if on else None
         return self
 
-    def in_flight(self, depth=2):
+    def in_flight(self, depth=2, lean_sampling=None):
         """Queue that keeps `depth` inference forwards in flight on their own streams, so that
         the next batch's sampling chain runs under this batch's SA/FP kernels (graphs.InFlight)."""
         from . import graphs
-        return graphs.InFlight(self, depth)
+        return graphs.InFlight(self, depth, lean_sampling)
 
     def forward(self, data_dict):
         g = getattr(self, "_graphed", None)
@@ -374,11 +374,11 @@ class VoteNetDetector(nn.Module):
         self._graphed = self._graph_runner if on else None
         return self
 
-    def in_flight(self, depth=2):
+    def in_flight(self, depth=2, lean_sampling=None):
         """Queue that keeps `depth` inference forwards in flight on their own streams, so that
         the next batch's sampling chain runs under this batch's SA/FP kernels (graphs.InFlight)."""
         from . import graphs
-        return graphs.InFlight(self, depth)
+        return graphs.InFlight(self, depth, lean_sampling)
 
     def forward(self, data_dict):
         g = getattr(self, "_graphed", None)

@@ -7,7 +7,9 @@ BN into the convolution weights is a handful of tiny torch device ops done once 
 (cached until .train() is called), packing to the kernel's bf16 shared-memory image is a
 kernel of the C ABI.
 """
+import contextlib
 import ctypes
+import threading
 
 import torch
 
@@ -204,10 +206,34 @@ def fps_grid_supported(n, npoint):
     return bool(N.lib().bqa_fps_grid_supported(int(n), int(npoint)))
 
 
-def furthest_point_sample_grid(xyz, npoint, grid):
+_mode = threading.local()
+
+
+def lean_sampling_enabled():
+    return bool(getattr(_mode, "lean", False))
+
+
+@contextlib.contextmanager
+def lean_sampling(on=True):
+    """Within this block furthest_point_sample_grid defaults to the throughput variant of the
+    sorted sampling kernel (fps_sorted.cu, kLean): half the SMs per scene, ~35 % more latency.
+    graphs.InFlight wraps its forwards in it; a single forward at a time should not."""
+    old = lean_sampling_enabled()
+    _mode.lean = bool(on)
+    try:
+        yield
+    finally:
+        _mode.lean = old
+
+
+def furthest_point_sample_grid(xyz, npoint, grid, lean=None):
     """(inds, new_xyz) == furthest_point_sample_with_xyz(xyz, npoint), computed over the cell grid
     `grid` = prebuild_ball_query_grid(xyz, ..., inline=True) with warp-level pruning
-    (fps_sorted.cu): bit-identical; 7-11 % less kernel time at 20k-100k points on B200."""
+    (fps_sorted.cu): bit-identical; 7-11 % less kernel time at 20k-100k points on B200.
+    lean=True: the throughput variant (coordinates in shared memory, half the SMs per scene,
+    more latency) for forwards that run several batches in flight; None = lean_sampling_enabled()."""
+    if lean is None:
+        lean = lean_sampling_enabled()
     N.check_tensor(xyz, "xyz", _f32)
     b, n, _ = xyz.shape
     m = int(npoint)
@@ -216,7 +242,8 @@ def furthest_point_sample_grid(xyz, npoint, grid):
     inds = torch.empty((b, m), dtype=torch.int32, device=xyz.device)
     new_xyz = torch.empty((b, m, 3), dtype=_f32, device=xyz.device)
     with torch.cuda.device(xyz.device):
-        N.call("bqa_furthest_point_sampling_grid", b, n, m, N.ptr(xyz), N.ptr(grid[0]), N.ptr(inds),
+        N.call("bqa_furthest_point_sampling_grid_lean" if lean else "bqa_furthest_point_sampling_grid",
+               b, n, m, N.ptr(xyz), N.ptr(grid[0]), N.ptr(inds),
                N.ptr(new_xyz), N.stream_ptr(xyz.device))
     return inds, new_xyz
 

@@ -105,10 +105,11 @@ def test_fps_vs_reference_extension(ref_ext):
         assert torch.equal(got, want), (b, n, m)
 
 
-def _fps_grid(xyz, m, radius=0.2):
+def _fps_grid(xyz, m, radius=0.2, lean=False):
     from bridgeqa_b200 import fused
     grid = fused.prebuild_ball_query_grid(xyz, radius, inline=True)
-    return fused.furthest_point_sample_grid(xyz, m, grid)
+    with fused.lean_sampling(lean):        # lean: the throughput variant (coordinates in shared memory)
+        return fused.furthest_point_sample_grid(xyz, m, grid)
 
 
 FPS_GRID_CASES = [
@@ -119,16 +120,18 @@ FPS_GRID_CASES = [
 ]
 
 
+@pytest.mark.parametrize("lean", [False, True])
 @pytest.mark.parametrize("b,n,m,r", FPS_GRID_CASES)
-def test_fps_grid_equals_plain_kernel(b, n, m, r):
+def test_fps_grid_equals_plain_kernel(b, n, m, r, lean):
     xyz = dev(scenes(b, n, first=51))
     want_i, want_x = ext.furthest_point_sampling(xyz, m, return_xyz=True)
-    got_i, got_x = _fps_grid(xyz, m, r)
+    got_i, got_x = _fps_grid(xyz, m, r, lean)
     assert torch.equal(got_i, want_i), (b, n, m)
     assert torch.equal(got_x, want_x)
 
 
-def test_fps_grid_matches_oracle_on_ties_and_skips(oracle_ops):
+@pytest.mark.parametrize("lean", [False, True])
+def test_fps_grid_matches_oracle_on_ties_and_skips(oracle_ops, lean):
     """Lattice clouds (exact ties every iteration: the carried tie key must reproduce the
     reference's pairwise tree), duplicates, the skip set, non-finite coordinates."""
     rng = np.random.RandomState(7)
@@ -139,18 +142,18 @@ def test_fps_grid_matches_oracle_on_ties_and_skips(oracle_ops):
     pts[1, 7] = [0.01, 0.02, 0.01]                    # |p|^2 <= 1e-3: never selectable
     pts[1, 0] = [0.0, 0.0, 0.0]                       # ... but index 0 is always the first sample
     want = oracle_ops.furthest_point_sampling(pts, 700)
-    got, _ = _fps_grid(dev(pts), 700, 0.25)
+    got, _ = _fps_grid(dev(pts), 700, 0.25, lean)
     np.testing.assert_array_equal(got.cpu().numpy(), want)
     # all points in the skip set -> every sample is index 0
     tiny = (rng.uniform(-0.01, 0.01, size=(1, 600, 3))).astype(np.float32)
-    got, got_x = _fps_grid(dev(tiny), 50, 0.2)
+    got, got_x = _fps_grid(dev(tiny), 50, 0.2, lean)
     assert (got == 0).all() and torch.equal(got_x[0, 5], dev(tiny)[0, 0])
     # NaN / inf coordinates: same behaviour as the plain kernel
     bad = scenes(1, 3000, first=3)
     bad[0, 11] = [np.nan, 1.0, 1.0]
     bad[0, 12] = [np.inf, 1.0, 1.0]
     want_i = ext.furthest_point_sampling(dev(bad), 200)
-    got_i, _ = _fps_grid(dev(bad), 200, 0.2)
+    got_i, _ = _fps_grid(dev(bad), 200, 0.2, lean)
     assert torch.equal(got_i, want_i)
 
 
