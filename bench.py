@@ -591,7 +591,7 @@ def main():
         traffic = None
         try:   # dram__bytes_read + dram__bytes_write per launch from the committed ncu --set full capture
             prof = json.load(open(os.path.join(ROOT, "profiles", "r1_kernels_ncu.json")))
-            names = {"bqa_furthest_point_sampling": "fps_cluster_kernel<14", "bqa_furthest_point_sampling_grid": "fps_sorted_kernel<14, 512",
+            names = {"bqa_furthest_point_sampling": "fps_cluster_kernel<14", "bqa_furthest_point_sampling_grid": "fps_sorted_kernel<14",
                      "bqa_furthest_point_sampling_grid_lean": "fps_sorted_kernel<18, 768"}
             if top and top["kernel"] in names and top["dims"][:3] == [BATCH, NUM_POINTS, 2048]:
                 hit = [k for k in prof if k["kernel"].startswith(names[top["kernel"]])]

@@ -53,6 +53,8 @@ class GraphedForward(object):
         ent = self.cache.get(key)
         if ent is None or ent["sig"] != sig:
             if len(self.cache) >= self.MAX_GRAPHS:
+                # the evicted graph (and the pool its buffers live in) may still be replaying
+                torch.cuda.synchronize(pc.device)
                 self.cache.pop(next(iter(self.cache)))
             ent = self._capture(pc, sig, bind)
             self.cache[key] = ent
