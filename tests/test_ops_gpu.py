@@ -117,6 +117,7 @@ FPS_GRID_CASES = [
     (2, 512, 256, 0.4), (3, 1000, 333, 0.2), (2, 2048, 1024, 0.4), (2, 5000, 600, 0.2),
     (2, 12345, 300, 0.05), (2, 20000, 512, 0.2), (4, 40000, 700, 0.2), (1, 40000, 2048, 3.0),
     (1, 70000, 96, 0.2), (1, 100000, 64, 0.2), (1, 147456, 40, 0.2),
+    (1, 60000, 64, 0.2), (1, 90000, 48, 0.2),      # throughput variant: clusters of 5 and 7 CTAs
 ]
 
 
