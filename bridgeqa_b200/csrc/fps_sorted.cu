@@ -74,10 +74,10 @@ __device__ unsigned long long g_active_warp_iters;
 // kLean = false: coordinates, running min-distances and tie keys in registers (125 registers x 512
 // threads: the CTA owns its SM), shared memory only holds a copy for the winner's lookup -- the
 // lowest latency per iteration.
-// kLean = true (the throughput variant, T = 1024): only the running min-distances stay in
+// kLean = true (the throughput variant, T = 768): only the running min-distances stay in
 // registers; coordinates and tie keys are read from the shared-memory copy {x, y, z, key} by the
-// few warps whose box the new sample can reach.  A 40k-point scene then fits THREE SMs (14336
-// points x 16 bytes = 224 KB each) instead of six, at ~15 % more latency per iteration: with
+// few warps whose box the new sample can reach.  A 40k-point scene then fits THREE SMs (13824
+// points x 16 bytes = 221 KB each) instead of six, at ~35 % more latency per iteration: with
 // several batches in flight (graphs.InFlight) the chain is not the bottleneck, SM-time is.
 template <int P, int T, bool kLean>
 __global__ void __launch_bounds__(T, 1)
@@ -301,7 +301,7 @@ bool fps_sorted_supported(int n, int m) {
   return n >= 512 && m >= 1 && (long long)n <= 16ll * kT * kMaxP;
 }
 
-// throughput variant: scenes of up to 8 x 14336 points (a portable cluster of lean CTAs)
+// throughput variant: scenes of up to 8 x 13824 points (a portable cluster of lean CTAs)
 constexpr int kLeanT = 768, kLeanMaxP = 18;
 bool fps_lean_supported(int n, int m) {
   return n >= 512 && m >= 1 && (long long)n <= 8ll * kLeanT * kLeanMaxP;

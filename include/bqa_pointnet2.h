@@ -65,9 +65,9 @@ BQA_API int bqa_furthest_point_sampling_grid(int b, int n, int m, const float *x
                                              int *idxs, float *new_xyz, void *stream);
 /* Same result, bit for bit, from the THROUGHPUT variant of that kernel: only the running
  * min-distances stay in registers, coordinates and tie keys are read from shared memory by the
- * warps that do update, so a scene occupies ceil(n / 14336) SMs (3 for 40k points) instead of 6
- * at ~15 % more latency per iteration.  Meant for several batches in flight, where SM-time and not
- * the latency of one chain bounds the throughput.  n > 114688 runs the kernel above.  */
+ * warps that do update, so a scene occupies ceil(n / 13824) SMs (3 for 40k points) instead of 6
+ * at ~35 % more latency per iteration (0.81 vs 0.61 us at 16 x 40k on B200).  Meant for several batches in flight, where SM-time and not
+ * the latency of one chain bounds the throughput.  n > 110592 runs the kernel above.  */
 BQA_API int bqa_furthest_point_sampling_grid_lean(int b, int n, int m, const float *xyz, const void *grid,
                                                   int *idxs, float *new_xyz, void *stream);
 

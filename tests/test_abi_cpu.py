@@ -80,6 +80,27 @@ def test_ops_refuse_cpu_tensors_no_fallback():
             call()
 
 
+def test_in_flight_queue_host_logic():
+    """graphs.InFlight: argument checks, default choice of the sampling variant, the thread-local
+    lean_sampling switch; submitting a CPU cloud raises (no CPU path)."""
+    from bridgeqa_b200 import detector, fused, graphs
+    net = detector.Pointnet2Backbone(input_feature_dim=1)
+    with pytest.raises(ValueError):
+        net.in_flight(0)
+    assert net.in_flight(1).lean is False and net.in_flight(3).lean is True
+    assert net.in_flight(3, lean_sampling=False).lean is False
+    assert isinstance(net.in_flight(2), graphs.InFlight)
+    assert not fused.lean_sampling_enabled()
+    with fused.lean_sampling():
+        assert fused.lean_sampling_enabled()
+        with fused.lean_sampling(False):
+            assert not fused.lean_sampling_enabled()
+        assert fused.lean_sampling_enabled()
+    assert not fused.lean_sampling_enabled()
+    with pytest.raises(RuntimeError, match="CUDA"):
+        net.in_flight(2).submit({"point_clouds": torch.zeros(1, 1024, 4)})
+
+
 def test_product_never_imports_oracle():
     pkg = os.path.join(ROOT, "bridgeqa_b200")
     for dirpath, _, files in os.walk(pkg):
