@@ -269,14 +269,20 @@ def run_train_mode(args, torch, dist, device, world, rank, real_stdout):
             dist.barrier()
             torch.cuda.synchronize()
 
+    # the next batch's SA1 sampling (coordinates only) is issued under this step's backward
+    nxt = None if args.no_prefetch else pc
+    from bridgeqa_b200 import fused as _fused
     for _ in range(args.warmup):
-        training.train_step(net, loss_fn, pc)
+        training.train_step(net, loss_fn, pc, next_point_clouds=nxt)
     barrier()
     l0 = _native.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(args.steps):
-        loss = training.train_step(net, loss_fn, pc)
+        loss = training.train_step(net, loss_fn, pc, next_point_clouds=nxt)
+    # K steps = K samplings inside the timed region: the first consumed the warm-up's prefetch,
+    # the last one's prefetch has to finish before the clock stops
+    torch.cuda.current_stream(device).wait_stream(_fused.side_stream(device, "prefetch"))
     e1.record()
     barrier()
     t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=device)
@@ -322,7 +328,8 @@ def run_train_mode(args, torch, dist, device, world, rank, real_stdout):
                 "config": {"workload": "VoteNetDetector fwd+bwd, train-mode BN, %d scenes/GPU: sm_100a operators "
                                        "(sampling, grid ball query, grouping, BatchNorm+ReLU+max fwd/bwd) + cuDNN "
                                        "TF32 1x1 convs, one flat NCCL all-reduce of %d fp32 gradients" % (bsz, nparam),
-                           "fused_bn_relu": bool(__import__("bridgeqa_b200.train_fused", fromlist=["x"]).enabled())},
+                           "fused_bn_relu": bool(__import__("bridgeqa_b200.train_fused", fromlist=["x"]).enabled()),
+                           "sampling_prefetch": not args.no_prefetch},
                 "kernels": kernels, "kernel_pass_ms": round(kpass_ms, 3),
                 "gpu_launches": launches, "loss": float(loss)}
         sys.stdout.flush()
@@ -351,6 +358,8 @@ def main():
     ap.add_argument("--mode", default="forward", choices=["forward", "train"],
                     help="forward = BASELINE headline (configs[1]); train = DET train step, configs[3]")
     ap.add_argument("--train-batch", type=int, default=16, help="scenes per GPU in --mode train")
+    ap.add_argument("--no-prefetch", action="store_true", help="--mode train: sample each batch in front of its "
+                    "forward instead of under the previous step's backward")
     ap.add_argument("--torch-bn", action="store_true", help="--mode train: torch BatchNorm/ReLU/max_pool modules "
                     "instead of the sm_100a streaming kernels (the reference's module structure)")
     ap.add_argument("--in-flight", type=int, default=4,

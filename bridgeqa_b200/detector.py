@@ -107,6 +107,45 @@ class Pointnet2Backbone(nn.Module):
                 cur = new_xyz
         return out
 
+    def prefetch_sampling(self, point_clouds):
+        """SA1's sampling of a FUTURE batch (cell grid + furthest point sampling: coordinates
+        only, no weights involved) issued now on a side stream, so that it runs underneath
+        whatever the current stream does next -- in training, the current step's backward.  The
+        forward of exactly this tensor (same storage, same version) then picks the result up
+        instead of sampling in front of SA1.  Uses the throughput variant of the sampling
+        kernel (3 SMs per 40k-point scene); indices are the same bits either way."""
+        pc = point_clouds
+        sa = self.sa1
+        if not (torch.is_tensor(pc) and pc.is_cuda and fused.enabled() and self.fps_grid
+                and fused.fps_grid_supported(pc.size(1), sa.npoint)):
+            return False
+        dev = pc.device
+        main = torch.cuda.current_stream(dev)
+        side = fused.side_stream(dev, "prefetch")
+        ready = torch.cuda.Event()
+        ready.record(main)
+        with torch.cuda.stream(side), torch.no_grad(), fused.lean_sampling(True):
+            side.wait_event(ready)
+            xyz = pc[..., :3].contiguous()
+            grid = fused.prebuild_ball_query_grid(xyz, sa.radius, inline=True)
+            inds, new_xyz = fused.furthest_point_sample_grid(xyz, sa.npoint, grid)
+            done = torch.cuda.Event()
+            done.record(side)
+        pc.record_stream(side)
+        self._prefetched = {"key": (pc.data_ptr(), pc._version, tuple(pc.shape)), "xyz": xyz, "grid": grid,
+                            "inds": inds, "new_xyz": new_xyz, "done": done}
+        return True
+
+    def _take_prefetched(self, pc):
+        pre, self._prefetched = getattr(self, "_prefetched", None), None
+        if pre is None or pre["key"] != (pc.data_ptr(), pc._version, tuple(pc.shape)):
+            return None
+        main = torch.cuda.current_stream(pc.device)
+        main.wait_event(pre["done"])
+        for t in (pre["xyz"], pre["grid"][0], pre["inds"], pre["new_xyz"]):
+            t.record_stream(main)
+        return pre
+
     def enable_cuda_graph(self, on=True, bind_inputs=False):
         """Inference forwards of a fixed input shape replay a captured CUDA graph (graphs.py);
         the returned tensors are then static buffers the next call overwrites."""
@@ -178,10 +217,14 @@ class Pointnet2Backbone(nn.Module):
             # levels 2-4 still goes through the parallel identity-prefix proof
             outs = []
             flags = None
+            pre = self._take_prefetched(data_dict["point_clouds"]) if xyz.is_cuda and not xyz.requires_grad else None
             for k, sa in enumerate((self.sa1, self.sa2, self.sa3, self.sa4)):
                 inds = new_xyz = grid = None
                 plain = xyz.is_cuda and not xyz.requires_grad
-                if k == 0 and plain and self.fps_grid and fused.enabled() \
+                if k == 0 and pre is not None:
+                    # sampled ahead of time under the previous step's backward (prefetch_sampling)
+                    grid, inds, new_xyz = pre["grid"], pre["inds"], pre["new_xyz"]
+                elif k == 0 and plain and self.fps_grid and fused.enabled() \
                         and fused.fps_grid_supported(xyz.size(1), sa.npoint):
                     # SA1: one cell grid serves the pruned sampling and the ball query
                     grid = fused.prebuild_ball_query_grid(xyz, sa.radius, inline=True)

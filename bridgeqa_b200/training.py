@@ -28,9 +28,14 @@ class ProjectionLoss(torch.nn.Module):
         return a.pow(2).mean() + b.pow(2).mean() + c.pow(2).mean()
 
 
-def train_step(model, loss_fn, point_clouds, optimizer=None):
+def train_step(model, loss_fn, point_clouds, optimizer=None, next_point_clouds=None):
     """One fwd + bwd (+ gradient all-reduce when a process group is up, + optimizer step).
-    Returns the detached loss."""
+    Returns the detached loss.
+
+    next_point_clouds: the batch the NEXT call will be given (already on the device).  Its SA1
+    sampling -- 1.3 ms of serial chain that depends on coordinates only, not on the weights this
+    step updates -- is issued on a side stream before this step's backward and runs underneath it
+    (Pointnet2Backbone.prefetch_sampling); the next forward picks it up."""
     model.train()
     if optimizer is not None:
         optimizer.zero_grad(set_to_none=True)
@@ -39,6 +44,10 @@ def train_step(model, loss_fn, point_clouds, optimizer=None):
             p.grad = None
     out = model({"point_clouds": point_clouds})
     loss = loss_fn(out)
+    if next_point_clouds is not None:
+        backbone = getattr(model, "detection_backbone", model)
+        if hasattr(backbone, "prefetch_sampling"):
+            backbone.prefetch_sampling(next_point_clouds)
     loss.backward()
     if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
         D.allreduce_gradients(model)

@@ -365,6 +365,39 @@ def test_cuda_graph_replay_equals_eager(which, c, _restore_fused):
         assert not torch.equal(out[keys[0]], eager[0][keys[0]])
 
 
+def test_training_sampling_prefetch_changes_nothing():
+    """Pointnet2Backbone.prefetch_sampling / train_step(next_point_clouds=...): SA1's sampling of
+    the next batch issued under this step's backward is picked up by the next forward (same
+    tensor only) and gives the same indices, loss and gradients as sampling in place."""
+    import copy
+    from bridgeqa_b200 import training
+    torch.manual_seed(0)
+    net_a = synthetic.fill_state_dict(detector.VoteNetDetector(4), seed=0).cuda()
+    net_b = copy.deepcopy(net_a)
+    loss_fn = training.ProjectionLoss().cuda()
+    pcs = [synthetic.make_batch(2, 20000, 4, first_scene=7 * i).cuda() for i in range(3)]
+    for i, pc in enumerate(pcs):
+        nxt = pcs[i + 1] if i + 1 < len(pcs) else None
+        la = training.train_step(net_a, loss_fn, pc, next_point_clouds=nxt)
+        bb = net_a.detection_backbone
+        assert (getattr(bb, "_prefetched", None) is not None) == (nxt is not None)
+        lb = training.train_step(net_b, loss_fn, pc)
+        torch.testing.assert_close(la, lb, rtol=1e-4, atol=1e-6)
+        for (n1, p1), (_, p2) in zip(net_a.named_parameters(), net_b.named_parameters()):
+            if p1.grad is None:
+                assert p2.grad is None
+                continue
+            scale = float(p2.grad.abs().max()) + 1e-12
+            assert float((p1.grad - p2.grad).abs().max()) <= 2e-3 * scale, n1
+    # a prefetch for another tensor is dropped, not used
+    net_a.detection_backbone.prefetch_sampling(pcs[0])
+    net_a.eval()
+    with torch.no_grad():
+        ia = net_a({"point_clouds": pcs[1]})["sa1_inds"]
+        ib = net_b.eval()({"point_clouds": pcs[1]})["sa1_inds"]
+    assert torch.equal(ia, ib)
+
+
 @pytest.mark.parametrize("graph", [False, True])
 @pytest.mark.parametrize("depth", [1, 2, 3])
 def test_in_flight_forwards_equal_serial(graph, depth, _restore_fused):
