@@ -272,11 +272,15 @@ def run_train_mode(args, torch, dist, device, world, rank, real_stdout):
     # the next batch's SA1 sampling (coordinates only) is issued under this step's backward
     nxt = None if args.no_prefetch else pc
     from bridgeqa_b200 import fused as _fused
+    clocks = ClockSampler(int(os.environ.get("LOCAL_RANK", "0")))
+    if rank == 0:
+        clocks.start()
     for _ in range(args.warmup):
         training.train_step(net, loss_fn, pc, next_point_clouds=nxt)
     barrier()
     l0 = _native.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    clocks.mark_begin()
     e0.record()
     for _ in range(args.steps):
         loss = training.train_step(net, loss_fn, pc, next_point_clouds=nxt)
@@ -285,6 +289,8 @@ def run_train_mode(args, torch, dist, device, world, rank, real_stdout):
     torch.cuda.current_stream(device).wait_stream(_fused.side_stream(device, "prefetch"))
     e1.record()
     barrier()
+    clocks.mark_end()
+    clk = clocks.stop() if rank == 0 else None
     t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=device)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -330,6 +336,7 @@ def run_train_mode(args, torch, dist, device, world, rank, real_stdout):
                                        "TF32 1x1 convs, one flat NCCL all-reduce of %d fp32 gradients" % (bsz, nparam),
                            "fused_bn_relu": bool(__import__("bridgeqa_b200.train_fused", fromlist=["x"]).enabled()),
                            "sampling_prefetch": not args.no_prefetch},
+                "clocks": clk,
                 "kernels": kernels, "kernel_pass_ms": round(kpass_ms, 3),
                 "gpu_launches": launches, "loss": float(loss)}
         sys.stdout.flush()
