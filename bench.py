@@ -372,6 +372,10 @@ def main():
     ap.add_argument("--in-flight", type=int, default=4,
                     help="batches in flight (graphs.InFlight): consecutive steps are issued on a ring of this many "
                          "streams so the next batch's sampling chain runs under this batch's SA/FP kernels; 1 = serial")
+    ap.add_argument("--bind-cpu", action="store_true",
+                    help="bind this rank (and the pinned buffers it then allocates) to the CPUs NVML reports as "
+                         "local to its GPU -- for the end-to-end number at 8 GPUs, which is bound by host <-> device "
+                         "copies (experimental: not measured at 8 GPUs yet)")
     ap.add_argument("--precision", default="fp16", choices=["fp16", "bf16"],
                     help="operand format of the fused tensor-core kernels (fp32 accumulate)")
     args = ap.parse_args()
@@ -395,6 +399,15 @@ def main():
         raise SystemExit("bench.py needs a GPU: the product path has no CPU fallback")
     torch.cuda.set_device(local_rank)
     device = torch.device("cuda", local_rank)
+    cpu_binding = None
+    if args.bind_cpu:
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            pynvml.nvmlDeviceSetCpuAffinity(pynvml.nvmlDeviceGetHandleByIndex(local_rank))
+            cpu_binding = sorted(os.sched_getaffinity(0))
+        except Exception as e:      # cpuset of the container may not contain the GPU's CPUs
+            cpu_binding = "failed: %r" % (e,)
     if world > 1:
         dist.init_process_group("nccl", device_id=device)
     args.warmup = max(args.warmup, 3)
@@ -583,11 +596,15 @@ def main():
         scenes = BATCH * world * args.steps
         value = scenes / (elapsed_ms / 1e3)
         kernels = []
+        kernel_time_ms = sum(d["ms"] for d in kern.values()) or 1.0
         for key, d in kern.items():
             w = algorithmic_work(d["name"], d["dims"])
             ms = d["ms"] / d["calls"]
+            # share: of the pass's elapsed time (streams overlap, the host leaves gaps);
+            # share_of_kernel_time: of the summed kernel times -- the figure an ncu launch list gives
             row = {"kernel": d["name"], "dims": d["dims"], "calls_per_step": d["calls"] / args.steps,
-                   "ms": round(ms, 5), "share": round(d["ms"] / kernel_pass_ms, 4), "bound": w["bound"]}
+                   "ms": round(ms, 5), "share": round(d["ms"] / kernel_pass_ms, 4),
+                   "share_of_kernel_time": round(d["ms"] / kernel_time_ms, 4), "bound": w["bound"]}
             if w["bound"] == "tensor":
                 ach = w["flops"] / (ms / 1e3) / 1e12
                 peak = peaks["bf16_tflops_sustained"]
@@ -622,7 +639,8 @@ def main():
                         "traffic_source": "profiles/r1_kernels_ncu.json (ncu --set full, per launch)" if traffic else None,
                         "algorithmic_bytes": algorithmic_work(top["kernel"], top["dims"])["bytes"],
                         "peak_source": peaks["source"],
-                        "share_of_step": top["share"], "ms": top["ms"]}
+                        "share_of_step": top["share"], "share_of_kernel_time": top["share_of_kernel_time"],
+                        "ms": top["ms"]}
             if "us_per_iter" in top:
                 roofline["us_per_iter"] = top["us_per_iter"]
                 roofline["note"] = ("FPS is a serial chain of npoint-1 cluster-wide argmax steps: "
@@ -644,7 +662,7 @@ def main():
                              % (ROT, ROT * h2d_bytes / 1e6),
                        "fused": any(r["bound"] == "tensor" for r in kernels), "torch_tf32": bool(args.tf32),
                        "cuda_graph": not args.no_graph,
-                       "in_flight": depth, "lean_sampling": bool(queue.lean),
+                       "in_flight": depth, "lean_sampling": bool(queue.lean), "cpu_binding": cpu_binding,
                        "in_flight_note": "consecutive steps are issued on a ring of %d streams (graphs.InFlight): each step "
                                          "is still one forward over one batch of 16 scenes; the next batch's sampling chain "
                                          "(latency-bound; throughput variant of the kernel: 48 SMs) runs under this batch's SA/FP kernels; "
