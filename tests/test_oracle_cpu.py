@@ -74,6 +74,68 @@ def test_fps_oracle_equals_literal_kernel_simulation(oracle_ops, n, m):
     np.testing.assert_array_equal(got, want)
 
 
+def _cell_order(xyz, h):
+    """A cell-sorted order like ball_query_grid.cu's counting sort (any spatially coherent order
+    exercises the rule; the exact cell function does not matter for soundness)."""
+    c = np.floor((xyz - xyz.min(0)) / np.float32(h)).astype(np.int64)
+    key = (c[:, 2] * 4096 + c[:, 1]) * 4096 + c[:, 0]
+    return np.argsort(key, kind="stable")
+
+
+@pytest.mark.parametrize("n,m,run,scale", [(8192, 300, 448, 1.0), (8192, 300, 576, 1.0), (6000, 200, 64, 1.0),
+                                           (8192, 200, 576, 1000.0), (4096, 150, 32, 1e-2)])
+def test_fps_pruning_rule_is_sound(oracle_ops, n, m, run, scale):
+    """The skip rule of fps_sorted.cu, replayed on the CPU: a warp holding a run of cell-sorted points
+    with bounding box [lo, hi] skips an iteration when  lb * 0.99999f >= wmax  (lb = fp32 squared
+    distance from the new sample to the box, wmax = max running min-distance of the run).  Sound
+    means: in every skipped (iteration, run) NO point's min-distance would have changed, i.e. the
+    fp32 distance the reference computes is >= the stored one for every point of the run.  Checked
+    against the full update with the reference's arithmetic (fma emulated exactly), on duplicates,
+    skip-set points, large and tiny coordinate scales; the samples come from the C oracle."""
+    f32 = np.float32
+    xyz = (scenes(1, n, first=17)[0] * f32(scale)).astype(np.float32)
+    xyz[5:40] = xyz[5]                                        # duplicates (zero-size boxes inside runs)
+    xyz[100:108] = f32(0.004) * f32(min(scale, 1.0))          # |p|^2 <= 1e-3: never updated, never picked
+    inds = oracle_ops.furthest_point_sampling(xyz[None], m)[0]
+    order = _cell_order(xyz, 0.2 * scale)
+    pts = xyz[order]
+    pos = np.empty(n, dtype=np.int64)
+    pos[order] = np.arange(n)                                 # original index -> position in the sorted order
+    x, y, z = (pts[:, i].astype(np.float64) for i in range(3))
+    mag = (z * z + (x * x + (y * y).astype(f32).astype(np.float64)).astype(f32).astype(np.float64)).astype(f32)
+    selectable = ~(mag.astype(np.float64) <= 1e-3)
+    td = np.where(selectable, f32(1e10), f32(-np.inf)).astype(np.float32)
+    nrun = (n + run - 1) // run
+    pad = nrun * run - n
+    def runs(a, fill):
+        return np.concatenate([a, np.full(pad, fill, a.dtype)]).reshape(nrun, run)
+    lo = np.stack([runs(pts[:, i], f32(np.inf)).min(1) for i in range(3)], 1)
+    hi = np.stack([runs(pts[:, i], f32(-np.inf)).max(1) for i in range(3)], 1)
+    wmax = np.full(nrun, np.inf, dtype=np.float32)            # inf: not evaluated yet
+    skipped = total = 0
+    for j in range(1, m):
+        s = xyz[inds[j - 1]]
+        dx = (pts[:, 0] - s[0]).astype(np.float64)
+        dy = (pts[:, 1] - s[1]).astype(np.float64)
+        dz = (pts[:, 2] - s[2]).astype(np.float64)
+        d = (dz * dz + (dx * dx + (dy * dy).astype(f32).astype(np.float64)).astype(f32).astype(np.float64)).astype(f32)
+        would_change = selectable & (d < td)                  # fminf(d, td) != td
+        e = np.maximum(np.maximum(lo - s, s - hi), f32(0)).astype(np.float32)
+        lb = (e[:, 0] * e[:, 0] + e[:, 1] * e[:, 1] + e[:, 2] * e[:, 2]).astype(np.float32)
+        skip = lb * f32(0.99999) >= wmax
+        changed_runs = runs(would_change, False).any(1)
+        assert not (skip & changed_runs).any(), "iteration %d: a skipped run had a point to update" % j
+        td = np.where(would_change, d, td)
+        # runs that did the update refresh their max (the kernel's wmax); -inf when nothing is selectable
+        new_max = runs(td, f32(-np.inf)).max(1)
+        wmax = np.where(skip, wmax, new_max).astype(np.float32)
+        skipped += int(skip.sum())
+        total += nrun
+        # the replay's arithmetic is the oracle's: its next sample holds the maximal min-distance
+        assert td[pos[inds[j]]] == td.max(), j
+    assert skipped > 0.3 * total, "the rule was hardly exercised (%d of %d)" % (skipped, total)
+
+
 def test_opt_n_threads_rule(oracle_ops):
     for n, want in [(1, 1), (2, 2), (3, 2), (511, 256), (512, 512), (513, 512), (1024, 512),
                     (2048, 512), (20000, 512), (40000, 512), (100000, 512)]:
