@@ -136,6 +136,68 @@ def test_fps_pruning_rule_is_sound(oracle_ops, n, m, run, scale):
     assert skipped > 0.3 * total, "the rule was hardly exercised (%d of %d)" % (skipped, total)
 
 
+def _prefix_proof_flag(xyz, m):
+    """CPU statement of fps_prefix_v_kernel + fps_prefix_check_kernel (csrc/fps.cu): 0 = the sampling of
+    this cloud is PROVABLY the identity prefix, 1 = not provable."""
+    f32 = np.float32
+    n = xyz.shape[0]
+    p = xyz.astype(np.float64)
+
+    def sq(a, b):                                             # fma(dz,dz,fma(dx,dx,dy*dy)), exact emulation
+        d = a - b
+        return (d[..., 2] * d[..., 2]
+                + (d[..., 0] * d[..., 0] + (d[..., 1] * d[..., 1]).astype(f32).astype(np.float64)).astype(f32)
+                .astype(np.float64)).astype(f32)
+
+    mag = (p[:, 2] * p[:, 2] + (p[:, 0] * p[:, 0] + (p[:, 1] * p[:, 1]).astype(f32).astype(np.float64))
+           .astype(f32).astype(np.float64)).astype(f32)
+    if (mag[1:].astype(np.float64) <= 1e-3).any():
+        return 1
+    r = np.full(n, 1e10, dtype=np.float32)                    # R(k, j) for the current j
+    for j in range(1, m):
+        r = np.minimum(r, sq(p, p[j - 1]))                    # now min over i < j
+        v = r[j]                                              # V[j]
+        if not v > 0:
+            return 1
+        if j + 1 < n and not (r[j + 1:] < v).all():
+            return 1
+    return 0
+
+
+def test_fps_prefix_proof_is_sound(oracle_ops):
+    """The parallel proof that replaces the SA2-4 sampling chains: whenever the proof
+    accepts a cloud, the oracle's furthest point sampling of every prefix of it to every m' <= m IS
+    the identity prefix; generic sampled clouds are accepted (the test is not vacuous), skip-set points
+    are always rejected, tie-ridden lattices are rejected or still identity."""
+    base = scenes(1, 6000, first=23)[0]
+    order = oracle_ops.furthest_point_sampling(base[None], 1024)[0]
+    cloud = base[order]                                        # a cloud in sampling order, like SA2's input
+    m = 512
+    assert _prefix_proof_flag(cloud, m) == 0
+    for n2, m2 in [(1024, 512), (1024, 100), (700, 512), (512, 512), (513, 256)]:
+        got = oracle_ops.furthest_point_sampling(cloud[None, :n2], m2)[0]
+        np.testing.assert_array_equal(got, np.arange(m2))
+    bad = cloud.copy()
+    bad[300] = [0.01, 0.01, 0.02]                              # |p|^2 <= 1e-3
+    assert _prefix_proof_flag(bad, m) == 1
+    # a far-away point late in the cloud breaks the order: must be rejected
+    far = cloud.copy()
+    far[900] = far[0] + np.float32(50.0)
+    assert _prefix_proof_flag(far, m) == 1
+    assert not np.array_equal(oracle_ops.furthest_point_sampling(far[None], m)[0], np.arange(m))
+    # lattices (exact ties everywhere): whatever the proof says must be true
+    rng = np.random.default_rng(3)
+    for trial in range(6):
+        g = rng.integers(0, 6, (400, 3)).astype(np.float32) * np.float32(0.5) + np.float32(1.0)
+        g = np.unique(g, axis=0)
+        rng.shuffle(g)
+        o = oracle_ops.furthest_point_sampling(g[None], len(g))[0]
+        lat = g[o]
+        mm = min(64, len(lat))
+        if _prefix_proof_flag(lat, mm) == 0:
+            np.testing.assert_array_equal(oracle_ops.furthest_point_sampling(lat[None], mm)[0], np.arange(mm))
+
+
 def test_opt_n_threads_rule(oracle_ops):
     for n, want in [(1, 1), (2, 2), (3, 2), (511, 256), (512, 512), (513, 512), (1024, 512),
                     (2048, 512), (20000, 512), (40000, 512), (100000, 512)]:
