@@ -38,16 +38,64 @@ def install(level="modules"):
                       ("pointnet2_modules", pointnet2_modules)):
         sys.modules[name] = mod
         sys.modules["lib.pointnet2." + name] = mod
-    lib = sys.modules.get("lib")
-    if lib is None:
-        lib = types.ModuleType("lib")
-        lib.__path__ = []
-        sys.modules["lib"] = lib
-    sub = sys.modules.get("lib.pointnet2")
-    if sub is None:
-        sub = types.ModuleType("lib.pointnet2")
-        sub.__path__ = []
-        sys.modules["lib.pointnet2"] = sub
-        lib.pointnet2 = sub
+    # `lib` and `lib.pointnet2` must stay the reference's REAL packages whenever they can be
+    # found (lib.loss_helper, lib.dataset, lib.solver, lib.config ... are imported by the
+    # reference's training / QA entry points): only the three submodule entries are overridden.
+    lib = _real_or_synthetic_package("lib", None)
+    sub = _real_or_synthetic_package("lib.pointnet2", lib)
     sub.pointnet2_utils, sub.pointnet2_modules, sub.pytorch_utils = (
         pointnet2_utils, pointnet2_modules, pytorch_utils)
+
+
+def _find_package_dir(name):
+    """Directory of package `name` (dotted) on sys.path / the cwd, without importing it."""
+    import os
+    rel = os.path.join(*name.split("."))
+    for base in list(sys.path) + [os.getcwd()]:
+        d = os.path.join(base or os.getcwd(), rel)
+        if os.path.isdir(d) and (os.path.exists(os.path.join(d, "__init__.py")) or name == "lib"):
+            return d
+    return None
+
+
+def _real_or_synthetic_package(name, parent):
+    """sys.modules[name]: the already imported package, else the real one from disk (imported
+    through importlib so its own __init__ runs), else -- reference tree not importable yet -- a
+    synthetic package whose __path__ is re-resolved lazily, so that `import lib.loss_helper`
+    still finds the reference's files once its root is on sys.path."""
+    import importlib
+    mod = sys.modules.get(name)
+    if mod is None and _find_package_dir(name) is not None:
+        try:
+            mod = importlib.import_module(name)
+        except Exception:
+            mod = None
+    if mod is None:
+        mod = types.ModuleType(name)
+        mod.__path__ = _LazyPath(name)
+        sys.modules[name] = mod
+    if parent is not None:
+        setattr(parent, name.rsplit(".", 1)[1], mod)
+    return mod
+
+
+class _LazyPath(list):
+    """__path__ of a synthetic package: looks the real directory up on every import, so the
+    shim can be installed before the reference root is put on sys.path."""
+
+    def __init__(self, name):
+        super().__init__()
+        self._name = name
+
+    def _dirs(self):
+        d = _find_package_dir(self._name)
+        return [d] if d else []
+
+    def __iter__(self):
+        return iter(self._dirs())
+
+    def __len__(self):
+        return len(self._dirs())
+
+    def __getitem__(self, i):
+        return self._dirs()[i]

@@ -31,6 +31,10 @@ constexpr int kChunk = 16384;              // elements of one (b, c) row per CTA
 
 struct Affine { float a, b, mean, invstd; };
 
+// torch's ReLU propagates NaN (threshold: x <= 0 ? 0 : x); fmaxf(x, 0) would turn a NaN activation
+// into 0 and hide a diverging run
+__device__ __forceinline__ float relu_nan(float v) { return v > 0.f ? v : (v != v ? v : 0.f); }
+
 __device__ __forceinline__ Affine affine_of(int c, const float *mean, const float *invstd,
                                             const float *gamma, const float *beta) {
   Affine f;
@@ -67,6 +71,9 @@ bn_stats_kernel(int c, long long l, const float *__restrict__ y, double *__restr
   const float *row = y + ((size_t)blockIdx.z * c + ch) * l;
   const long long i0 = (long long)blockIdx.x * kChunk;
   const long long i1 = min(l, i0 + kChunk);
+  // sums are taken around a per-channel shift K (the channel's first element): E[(y-K)^2] - E[y-K]^2
+  // does not cancel catastrophically when |mean| >> std, which E[y^2] - E[y]^2 in fp32 does
+  const float K = __ldg(y + (size_t)ch * l);
   float s1 = 0.f, s2 = 0.f;
   if ((l & 3) == 0) {
     const float4 *r4 = reinterpret_cast<const float4 *>(row);
@@ -80,12 +87,14 @@ bn_stats_kernel(int c, long long l, const float *__restrict__ y, double *__restr
       for (int u = 0; u < 4; ++u) v[u] = __ldg(r4 + i + u * kThreads);
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
+        v[u].x -= K; v[u].y -= K; v[u].z -= K; v[u].w -= K;
         a1[u] += (v[u].x + v[u].y) + (v[u].z + v[u].w);
         a2[u] += (v[u].x * v[u].x + v[u].y * v[u].y) + (v[u].z * v[u].z + v[u].w * v[u].w);
       }
     }
     for (; i < e4; i += kThreads) {
-      const float4 v = __ldg(r4 + i);
+      float4 v = __ldg(r4 + i);
+      v.x -= K; v.y -= K; v.z -= K; v.w -= K;
       a1[0] += (v.x + v.y) + (v.z + v.w);
       a2[0] += (v.x * v.x + v.y * v.y) + (v.z * v.z + v.w * v.w);
     }
@@ -93,7 +102,7 @@ bn_stats_kernel(int c, long long l, const float *__restrict__ y, double *__restr
     s2 = (a2[0] + a2[1]) + (a2[2] + a2[3]);
   } else {
     for (long long i = i0 + threadIdx.x; i < i1; i += kThreads) {
-      const float v = __ldg(row + i);
+      const float v = __ldg(row + i) - K;
       s1 += v;
       s2 += v * v;
     }
@@ -101,14 +110,16 @@ bn_stats_kernel(int c, long long l, const float *__restrict__ y, double *__restr
   block_add2(s1, s2, &sums[ch], &sums[c + ch]);
 }
 
-__global__ void bn_finalize_kernel(int c, double count, const double *__restrict__ sums, float eps,
+__global__ void bn_finalize_kernel(int c, long long l, double count, const float *__restrict__ y,
+                                   const double *__restrict__ sums, float eps,
                                    float momentum, float *__restrict__ mean, float *__restrict__ invstd,
                                    float *__restrict__ running_mean, float *__restrict__ running_var) {
   const int ch = blockIdx.x * blockDim.x + threadIdx.x;
   if (ch >= c) return;
-  const double m = sums[ch] / count;
-  double var = sums[c + ch] / count - m * m;
+  const double ms = sums[ch] / count;                 // mean of (y - K), K as in bn_stats_kernel
+  double var = sums[c + ch] / count - ms * ms;
   if (var < 0.0) var = 0.0;
+  const double m = (double)y[(size_t)ch * l] + ms;
   mean[ch] = (float)m;
   invstd[ch] = (float)(1.0 / sqrt(var + (double)eps));
   if (running_mean) running_mean[ch] = (1.f - momentum) * running_mean[ch] + momentum * (float)m;
@@ -132,12 +143,12 @@ bn_relu_apply_kernel(int c, long long l, const float *__restrict__ y, const floa
     float4 *o4 = reinterpret_cast<float4 *>(x + off);
     for (long long i = i0 / 4 + threadIdx.x; i < i1 / 4; i += kThreads) {
       const float4 v = __ldg(r4 + i);
-      o4[i] = make_float4(fmaxf(fmaf(v.x, f.a, f.b), 0.f), fmaxf(fmaf(v.y, f.a, f.b), 0.f),
-                          fmaxf(fmaf(v.z, f.a, f.b), 0.f), fmaxf(fmaf(v.w, f.a, f.b), 0.f));
+      o4[i] = make_float4(relu_nan(fmaf(v.x, f.a, f.b)), relu_nan(fmaf(v.y, f.a, f.b)),
+                          relu_nan(fmaf(v.z, f.a, f.b)), relu_nan(fmaf(v.w, f.a, f.b)));
     }
   } else {
     for (long long i = i0 + threadIdx.x; i < i1; i += kThreads)
-      x[off + i] = fmaxf(fmaf(__ldg(y + off + i), f.a, f.b), 0.f);
+      x[off + i] = relu_nan(fmaf(__ldg(y + off + i), f.a, f.b));
   }
 }
 
@@ -180,7 +191,7 @@ bn_relu_max_kernel(int c, int row4, int lpg_shift, const float *__restrict__ y,
     }
     if (e < row4 && (e & (lpg - 1)) == 0) {
       const size_t g = row * (size_t)(row4 >> lpg_shift) + (size_t)(e >> lpg_shift);
-      out[g] = fmaxf(best, 0.f);
+      out[g] = relu_nan(best);
       argmax[g] = bi;
     }
   }
@@ -333,7 +344,7 @@ int bn_stats_dispatch(int b, int c, long long l, const float *y, double *sums, f
   bn_stats_kernel<<<row_grid(b, c, l), kThreads, 0, stream>>>(c, l, y, sums);
   count_launch();
   if (int rc = check_launch("bn_stats_kernel")) return rc;
-  bn_finalize_kernel<<<ceil_div(c, 128), 128, 0, stream>>>(c, (double)b * (double)l, sums, eps, momentum,
+  bn_finalize_kernel<<<ceil_div(c, 128), 128, 0, stream>>>(c, l, (double)b * (double)l, y, sums, eps, momentum,
                                                           mean, invstd, running_mean, running_var);
   count_launch();
   return check_launch("bn_finalize_kernel");

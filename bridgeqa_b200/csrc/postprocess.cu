@@ -8,8 +8,11 @@
 // boxes are visited in descending score; a visited box that is still alive is picked and
 // suppresses every later box j whose overlap o = inter / (area_i + area_j - inter)  (or
 // inter / area_j with old_type) exceeds the threshold -- and, for the same-class variant, only if
-// cls_i == cls_j.  l, w, h = max(0, min(upper) - max(lower)).  Equal scores are ordered by index
-// (np.argsort leaves their order unspecified).
+// cls_i == cls_j.  l, w, h = max(0, min(upper) - max(lower)).  The reference walks np.argsort(score)
+// from its END; NumPy's default argsort leaves the order of equal scores unspecified (its AVX-512
+// sort is not stable even for 8 elements), so ties are resolved as a STABLE ascending argsort
+// walked from the end would: among equal scores the HIGHER index is visited first
+// (tests/golden/make_golden_post.py records both the default and the kind="stable" reference runs).
 #include "common.cuh"
 
 namespace bqa {
@@ -37,7 +40,7 @@ nms3d_kernel(int k, const float *__restrict__ boxes_all, const int *__restrict__
     if (i < k && (!valid || valid[i])) {
       const uint32_t u = __float_as_uint(boxes[i * 8 + 6]);
       const uint32_t ord = (u & 0x80000000u) ? ~u : (u | 0x80000000u);      // float order -> uint order
-      key = ((unsigned long long)(~ord) << 32) | (uint32_t)i;               // descending score, then index
+      key = ((unsigned long long)(~ord) << 32) | (uint32_t)(~(uint32_t)i);  // descending score, then descending index
     }
     keys[i] = key;
     if (i < k) { pick[i] = 0; if (order) order[i] = -1; }
@@ -63,7 +66,7 @@ nms3d_kernel(int k, const float *__restrict__ boxes_all, const int *__restrict__
       while (c < k && !alive[c]) ++c;
       s_cur = c;
       if (c < k) {
-        const int bi = (int)(uint32_t)keys[c];
+        const int bi = (int)(~(uint32_t)keys[c]);
         pick[bi] = 1;
         if (order) order[s_npick] = bi;
         ++s_npick;
@@ -72,14 +75,14 @@ nms3d_kernel(int k, const float *__restrict__ boxes_all, const int *__restrict__
     __syncthreads();
     const int c = s_cur;
     if (c >= k) break;
-    const int bi = (int)(uint32_t)keys[c];
+    const int bi = (int)(~(uint32_t)keys[c]);
     const double ix1 = boxes[bi * 8 + 0], iy1 = boxes[bi * 8 + 1], iz1 = boxes[bi * 8 + 2];
     const double ix2 = boxes[bi * 8 + 3], iy2 = boxes[bi * 8 + 4], iz2 = boxes[bi * 8 + 5];
     const float icls = boxes[bi * 8 + 7];
     const double iarea = __dmul_rn(__dmul_rn(ix2 - ix1, iy2 - iy1), iz2 - iz1);
     for (int p = c + 1 + tid; p < k; p += kNmsThreads) {
       if (!alive[p]) continue;
-      const int bj = (int)(uint32_t)keys[p];
+      const int bj = (int)(~(uint32_t)keys[p]);
       const double jx1 = boxes[bj * 8 + 0], jy1 = boxes[bj * 8 + 1], jz1 = boxes[bj * 8 + 2];
       const double jx2 = boxes[bj * 8 + 3], jy2 = boxes[bj * 8 + 4], jz2 = boxes[bj * 8 + 5];
       const double l = fmax(0.0, fmin(ix2, jx2) - fmax(ix1, jx1));

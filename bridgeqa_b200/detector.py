@@ -132,13 +132,15 @@ class Pointnet2Backbone(nn.Module):
             done = torch.cuda.Event()
             done.record(side)
         pc.record_stream(side)
-        self._prefetched = {"key": (pc.data_ptr(), pc._version, tuple(pc.shape)), "xyz": xyz, "grid": grid,
+        # the tensor itself is kept (not its address): a freed block can come back from the caching
+        # allocator at the same address with version 0 and would otherwise match a stale entry
+        self._prefetched = {"pc": pc, "version": pc._version, "xyz": xyz, "grid": grid,
                             "inds": inds, "new_xyz": new_xyz, "done": done}
         return True
 
     def _take_prefetched(self, pc):
         pre, self._prefetched = getattr(self, "_prefetched", None), None
-        if pre is None or pre["key"] != (pc.data_ptr(), pc._version, tuple(pc.shape)):
+        if pre is None or pre["pc"] is not pc or pre["version"] != pc._version:
             return None
         main = torch.cuda.current_stream(pc.device)
         main.wait_event(pre["done"])
@@ -168,12 +170,17 @@ class Pointnet2Backbone(nn.Module):
             return g(data_dict)
         return self._forward_impl(data_dict)
 
+    def train(self, mode=True):
+        self._prefetched = None
+        return super().train(mode)
+
     def _forward_impl(self, data_dict):
         xyz, features = self._break_up_pc(data_dict["point_clouds"])
 
         overlap = (fused.enabled() and xyz.is_cuda and not self.training
                    and not torch.is_grad_enabled())
         if overlap:
+            self._prefetched = None        # a prefetch is only ever consumed by the training branch
             main = torch.cuda.current_stream(xyz.device)
             # SA1: sampling slices on this stream, their ball query + MLP underneath on a side
             # stream; levels 2-4 are sampled on a second side stream as soon as SA1's centres exist
@@ -286,21 +293,46 @@ class DatasetConfig(object):
     """Stand-in for `data.scannet.model_util_scannet.ScannetDatasetConfig`, which the
     reference imports (models/proposal_module.py:11) from an un-vendored data tree (dangling
     symlink in /root/reference).  ScanNet boxes are axis-aligned: one heading bin whose angle
-    is always 0; 18 classes = 18 size clusters.  mean_size_arr is data (a .npz in the
-    original); here it defaults to ones and can be replaced."""
+    is always 0 (heading_mode="zero", the VoteNet/ScanRefer ScanNet config: class2angle_batch
+    returns zeros); heading_mode="bins" decodes `class * 2pi/num_heading_bin + residual`, wrapped
+    to (-pi, pi] (the SUN RGB-D style config of the same code base).  18 classes = 18 size
+    clusters.  mean_size_arr is data (a .npz in the original); here it defaults to ones and can
+    be replaced."""
 
-    def __init__(self, num_class=18, num_heading_bin=1, num_size_cluster=18, mean_size_arr=None):
+    def __init__(self, num_class=18, num_heading_bin=1, num_size_cluster=18, mean_size_arr=None,
+                 heading_mode="zero"):
+        if heading_mode not in ("zero", "bins"):
+            raise ValueError("heading_mode must be 'zero' or 'bins'")
         self.num_class = num_class
         self.num_heading_bin = num_heading_bin
         self.num_size_cluster = num_size_cluster
+        self.heading_mode = heading_mode
         self.mean_size_arr = (np.ones((num_size_cluster, 3), dtype=np.float32)
                               if mean_size_arr is None else np.asarray(mean_size_arr, dtype=np.float32))
 
     def class2angle(self, pred_cls, residual, to_label_format=True):
-        return 0
+        if self.heading_mode == "zero":
+            return 0
+        angle = pred_cls * (2 * np.pi / float(self.num_heading_bin)) + residual
+        if to_label_format and angle > np.pi:
+            angle = angle - 2 * np.pi
+        return angle
 
     def class2size(self, pred_cls, residual):
         return self.mean_size_arr[pred_cls] + residual
+
+
+def decode_heading(heading_scores, heading_residuals, heading_mode):
+    """Heading angle (B,K) as `param2obb_batch` hands it to get_3d_box_batch: the NEGATED
+    class2angle_batch(argmax class, its residual); all on the device."""
+    cls = torch.argmax(heading_scores, -1)
+    if heading_mode == "zero":
+        return torch.zeros(cls.shape, dtype=heading_residuals.dtype, device=cls.device)
+    nh = heading_scores.size(-1)
+    res = torch.gather(heading_residuals, 2, cls.unsqueeze(-1)).squeeze(-1)
+    angle = cls.to(res.dtype) * (2 * math.pi / float(nh)) + res
+    angle = torch.where(angle > math.pi, angle - 2 * math.pi, angle)
+    return -angle
 
 
 def box_corners(box_size, heading_angle, center):
@@ -321,8 +353,12 @@ class ProposalModule(nn.Module):
     """Vote aggregation (an SA layer over the votes) + proposal head + score decoding."""
 
     def __init__(self, num_class, num_heading_bin, num_size_cluster, mean_size_arr, num_proposal,
-                 sampling, seed_feat_dim=256, proposal_size=128, radius=0.3, nsample=16):
+                 sampling, seed_feat_dim=256, proposal_size=128, radius=0.3, nsample=16,
+                 heading_mode="zero"):
         super().__init__()
+        if heading_mode not in ("zero", "bins"):
+            raise ValueError("heading_mode must be 'zero' (ScanNet) or 'bins'")
+        self.heading_mode = heading_mode
         self.num_class = num_class
         self.num_heading_bin = num_heading_bin
         self.num_size_cluster = num_size_cluster
@@ -379,13 +415,16 @@ class ProposalModule(nn.Module):
     def decode_pred_box(self, data_dict):
         """Box corners (B, K, 8, 3) on the device.  The reference does this through
         .cpu().numpy() + param2obb_batch + get_3d_box_batch + .cuda()
-        (proposal_module.py:87-108), a host sync inside the forward; with ScanNet's single
-        zero-angle heading bin the result is center +- size/2, computed here in torch."""
+        (proposal_module.py:87-108; utils/box_util.py:302-325), a host sync inside the forward.
+        Same decode here in torch ops: size = mean_size[argmax size class] + its residual, heading
+        = -class2angle(argmax heading class, its residual) (0 for ScanNet's single bin), corners =
+        the 8 sign patterns rotated about y and shifted to the centre."""
         size_cls = torch.argmax(data_dict["size_scores"], -1)                       # (B,K)
         res = torch.gather(data_dict["size_residuals"], 2,
                            size_cls[..., None, None].expand(-1, -1, 1, 3)).squeeze(2)
         box_size = self._mean_size.to(res.device)[size_cls] + res
-        heading = torch.zeros_like(box_size[..., 0])      # class2angle == 0 for ScanNet
+        heading = decode_heading(data_dict["heading_scores"], data_dict["heading_residuals"],
+                                 self.heading_mode)
         return box_corners(box_size, heading, data_dict["center"])
 
 
@@ -406,7 +445,7 @@ class VoteNetDetector(nn.Module):
         self.proposal_net = ProposalModule(
             cfg.num_class, cfg.num_heading_bin, cfg.num_size_cluster, cfg.mean_size_arr,
             num_proposal, sampling, seed_feat_dim=seed_feat_dim, proposal_size=proposal_size,
-            radius=vote_radius, nsample=vote_nsample)
+            radius=vote_radius, nsample=vote_nsample, heading_mode=getattr(cfg, "heading_mode", "zero"))
 
     def enable_cuda_graph(self, on=True, bind_inputs=False):
         """See Pointnet2Backbone.enable_cuda_graph; here the whole detector forward is one graph."""

@@ -153,6 +153,14 @@ class InFlight(object):
         for ev in (after if isinstance(after, (list, tuple)) else (after,)):
             s.wait_event(ev)
         g = getattr(self.module, "_graphed", None)
+        if (g is not None and self.depth > 1 and g.applicable(data_dict)
+                and not (g.bind_inputs and pc.is_contiguous())):
+            # one shared staging buffer + one set of static outputs per shape: a second forward
+            # in flight would overwrite both while the first still runs
+            raise RuntimeError(
+                "in_flight(depth > 1) over a CUDA graph needs enable_cuda_graph(bind_inputs=True) and "
+                "contiguous inputs: with a shared staging buffer the forwards in flight would overwrite "
+                "each other's input and static outputs")
         with torch.cuda.stream(s), torch.no_grad(), fused.lean_sampling(self.lean):
             static = g is not None and g.applicable(data_dict)
             if not static:

@@ -207,3 +207,23 @@ def test_box_corners_match_numpy_formula():
     R[..., 2, 0] = -np.sin(ang); R[..., 2, 2] = np.cos(ang)
     want = np.matmul(c3, np.transpose(R, (0, 1, 3, 2))) + cen[..., None, :]
     np.testing.assert_allclose(got, want, rtol=1e-5, atol=1e-5)
+
+
+def test_decode_scores_equals_reference_fixture_on_cpu():
+    """Host logic of the on-device box decode (plain torch ops, so it also runs on CPU tensors)
+    against utils/box_util.get_3d_box_batch outputs recorded from the reference itself
+    (tests/golden/make_golden_post.py); the -m gpu twin is in test_postprocess_gpu.py."""
+    from bridgeqa_b200 import detector
+    G = np.load(os.path.join(os.path.dirname(__file__), "golden", "ref_postprocess.npz"))
+    for case in G["decode_cases"]:
+        p = "decode%d_" % case
+        hs, hr = G[p + "heading_scores"], G[p + "heading_residuals_normalized"]
+        ss, sr = G[p + "size_scores"], G[p + "size_residuals_normalized"]
+        k, nh, ns = hs.shape[0], hs.shape[1], ss.shape[1]
+        mod = detector.ProposalModule(18, nh, ns, G[p + "mean_size"], k, "vote_fps",
+                                      heading_mode=str(G[p + "mode"])).eval()
+        net = np.concatenate([np.zeros((k, 2), np.float32), G[p + "center"], hs, hr, ss, sr.reshape(k, ns * 3),
+                              np.zeros((k, 18), np.float32)], 1).T[None]
+        dd = {"aggregated_vote_xyz": torch.zeros(1, k, 3), "aggregated_vote_features": torch.zeros(1, k, 128)}
+        dd = mod.decode_scores(torch.from_numpy(np.ascontiguousarray(net)), dd)
+        np.testing.assert_allclose(dd["bbox_corner"][0].double().numpy(), G[p + "bbox_corner"], rtol=0, atol=5e-6)

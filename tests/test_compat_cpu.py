@@ -22,6 +22,11 @@ if %(level)r == "ext":
 from models.backbone_module import Pointnet2Backbone
 from models.voting_module import VotingModule
 import torch
+# the shims must not shadow the reference's real `lib` package: its other modules still import
+import lib, lib.loss
+assert os.path.samefile(os.path.dirname(lib.loss.__file__), os.path.join(%(ref)r, "lib")), lib.loss.__file__
+import importlib.util
+assert importlib.util.find_spec("lib.loss_helper") is not None and importlib.util.find_spec("lib.dataset") is not None
 net = Pointnet2Backbone(input_feature_dim=7)
 from bridgeqa_b200 import detector
 mine = detector.Pointnet2Backbone(input_feature_dim=7)
