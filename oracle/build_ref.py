@@ -44,11 +44,37 @@ def available():
     return os.path.exists(SO_PATH)
 
 
+# The reference's Python layer over the extension, staged UNMODIFIED (byte-for-byte copies, made at
+# build time into the git-ignored oracle/_ref/ only) so that the GPU box -- where /root/reference does
+# not exist -- can run the stock reference modules as the checker / the reference-on-GPU timing leg.
+REF_ROOT = "/root/reference"
+TREE_DIR = os.path.join(HERE, "_ref", "ref_tree")
+STAGED = ("lib/pointnet2/pointnet2_modules.py", "lib/pointnet2/pointnet2_utils.py",
+          "lib/pointnet2/pytorch_utils.py", "models/backbone_module.py", "models/voting_module.py")
+
+
+def stage_python_layer():
+    """Copies STAGED into oracle/_ref/ref_tree (same relative paths).  Returns the tree dir or None."""
+    import shutil
+    if not os.path.isdir(REF_ROOT):
+        return TREE_DIR if tree_available() else None
+    for rel in STAGED:
+        dst = os.path.join(TREE_DIR, rel)
+        os.makedirs(os.path.dirname(dst), exist_ok=True)
+        shutil.copyfile(os.path.join(REF_ROOT, rel), dst)
+    return TREE_DIR
+
+
+def tree_available():
+    return all(os.path.exists(os.path.join(TREE_DIR, rel)) for rel in STAGED)
+
+
 def build(force=False, verbose=True):
     """Returns the .so path, or None when /root/reference is absent (GPU box)."""
     if not os.path.isdir(REF_SRC):
         return SO_PATH if available() else None
     srcs = sorted(glob.glob(REF_SRC + "/src/*.cpp") + glob.glob(REF_SRC + "/src/*.cu"))
+    stage_python_layer()
     if available() and not force:
         newest = max(os.path.getmtime(s) for s in srcs)
         if os.path.getmtime(SO_PATH) >= newest:

@@ -158,3 +158,61 @@ def detector(point_clouds, sd, num_proposal=256, vote_radius=0.3, vote_nsample=1
     x = F.conv1d(x, sd[p + "6.weight"], sd[p + "6.bias"])
     out["proposal_scores"] = x.numpy()
     return out
+
+
+def proposal_head(aggregated_features, sd, prefix="proposal_net.proposal."):
+    """(B,128,K) np -> raw head output (B, 2+3+2nh+4ns+nc, K)  (models/proposal_module.py:43-56, 81)."""
+    p = prefix
+    x = _t(aggregated_features)
+
+    def bn(y, i):
+        return F.batch_norm(y, sd["%s%d.running_mean" % (p, i)], sd["%s%d.running_var" % (p, i)],
+                            sd["%s%d.weight" % (p, i)], sd["%s%d.bias" % (p, i)], False, 0.0, BN_EPS)
+
+    x = F.relu(bn(F.conv1d(x, sd[p + "0.weight"]), 1))
+    x = F.relu(bn(F.conv1d(x, sd[p + "3.weight"]), 4))
+    return F.conv1d(x, sd[p + "6.weight"], sd[p + "6.bias"]).numpy()
+
+
+def decode_scores(net, base_xyz, mean_size_arr, num_heading_bin=1, num_size_cluster=18, heading_mode="zero"):
+    """models/proposal_module.py:110-151 (decode_scores) + :87-108 (decode_pred_box) in NumPy:
+    slices of the transposed head output in float32 as torch does, then the box through
+    param2obb_batch (un-vendored data/scannet/model_util_scannet.py; its published form: size =
+    mean_size[class] + residual, heading = -class2angle_batch, 0 for ScanNet) and
+    utils/box_util.py:302-325 get_3d_box_batch in float64 (the reference's NumPy dtype)."""
+    nh, ns = num_heading_bin, num_size_cluster
+    t = np.ascontiguousarray(np.transpose(net, (0, 2, 1))).astype(np.float32)      # :115
+    b, k = t.shape[:2]
+    o = 5 + 2 * nh
+    out = {"objectness_scores": t[:, :, 0:2],                                       # :119
+           "center": (base_xyz.astype(np.float32) + t[:, :, 2:5]).astype(np.float32),   # :121-122
+           "heading_scores": t[:, :, 5:5 + nh],
+           "heading_residuals": (t[:, :, 5 + nh:o] * np.float32(np.pi / nh)).astype(np.float32),   # :136
+           "size_scores": t[:, :, o:o + ns],
+           "sem_cls_scores": t[:, :, o + 4 * ns:]}
+    srn = t[:, :, o + ns:o + 4 * ns].reshape(b, k, ns, 3)
+    mean_size = np.asarray(mean_size_arr, dtype=np.float32)
+    out["size_residuals"] = (srn * mean_size[None, None]).astype(np.float32)         # :139
+    hcls = out["heading_scores"].argmax(-1)                                         # :90
+    hres = np.take_along_axis(out["heading_residuals"], hcls[..., None], 2)[..., 0]
+    scls = out["size_scores"].argmax(-1)                                            # :94
+    sres = np.take_along_axis(out["size_residuals"], scls[..., None, None].repeat(3, -1), 2)[:, :, 0]
+    if heading_mode == "zero":
+        angle = np.zeros(hcls.shape)
+    else:
+        angle = hcls * (2 * np.pi / float(nh)) + hres
+        angle = np.where(angle > np.pi, angle - 2 * np.pi, angle)
+    heading = -angle.astype(np.float64)
+    size = (mean_size[scls] + sres).astype(np.float64)
+    centre = out["center"].astype(np.float64)
+    l, w, h = size[..., 0:1] / 2, size[..., 1:2] / 2, size[..., 2:3] / 2            # box_util.py:311-320
+    c3 = np.stack([np.concatenate((l, l, -l, -l, l, l, -l, -l), -1),
+                   np.concatenate((w, -w, -w, w, w, -w, -w, w), -1),
+                   np.concatenate((h, h, h, h, -h, -h, -h, -h), -1)], -1)
+    R = np.zeros(heading.shape + (3, 3))                                            # roty_batch :255-268
+    R[..., 0, 0] = np.cos(heading); R[..., 0, 2] = np.sin(heading); R[..., 1, 1] = 1
+    R[..., 2, 0] = -np.sin(heading); R[..., 2, 2] = np.cos(heading)
+    out["bbox_corner"] = np.matmul(c3, np.swapaxes(R, -1, -2)) + centre[..., None, :]   # :321-324
+    out["bbox_mask"] = out["objectness_scores"].argmax(-1)
+    out["bbox_sems"] = out["sem_cls_scores"].argmax(-1)
+    return out

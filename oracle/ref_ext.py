@@ -30,3 +30,35 @@ def load():
         print("oracle/_ref present but not importable: %r" % (e,))
         _mod = None
     return _mod
+
+
+def load_reference_modules(ext_module):
+    """The UNMODIFIED reference Python layer staged by build_ref.stage_python_layer(), imported on top
+    of `ext_module` as `pointnet2._ext` (the reference's own extension from load(), or any object with
+    the same 9 functions).  Returns (backbone_module, voting_module, pointnet2_utils) or None when the
+    tree is not staged.  The staged files do `sys.path.append(os.path.join(os.getcwd(), "lib"))`
+    (backbone_module.py:8) and `import pointnet2_utils` from their own directory, so the tree root is
+    put on sys.path and used as cwd for the import."""
+    import types
+    tree = os.path.join(HERE, "_ref", "ref_tree")
+    if not os.path.exists(os.path.join(tree, "models", "backbone_module.py")):
+        return None
+    pkg = types.ModuleType("pointnet2")
+    pkg.__path__ = []
+    pkg._ext = ext_module
+    sys.modules["pointnet2"] = pkg
+    sys.modules["pointnet2._ext"] = ext_module
+    for stale in ("pointnet2_utils", "pointnet2_modules", "pytorch_utils", "lib", "lib.pointnet2",
+                  "lib.pointnet2.pointnet2_modules", "lib.pointnet2.pointnet2_utils",
+                  "lib.pointnet2.pytorch_utils", "models", "models.backbone_module", "models.voting_module"):
+        sys.modules.pop(stale, None)
+    cwd = os.getcwd()
+    sys.path.insert(0, tree)
+    os.chdir(tree)
+    try:
+        backbone_module = importlib.import_module("models.backbone_module")
+        voting_module = importlib.import_module("models.voting_module")
+        utils = sys.modules["pointnet2_utils"]
+    finally:
+        os.chdir(cwd)
+    return backbone_module, voting_module, utils
