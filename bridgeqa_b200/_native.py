@@ -62,6 +62,12 @@ _SIGNATURES = {
     "bqa_fp_mlp_forward": ([_I, _I, _I, _I, _I, _P, _P, _P, _I, _P, _I, _I, _I, _P, _P, _P, _P, _P, _I, _P], _I),
     "bqa_pack_weight_16": ([_I, _I, _I, _I, _I, _P, _P, _P], _I),
     "bqa_sa_mlp_max_supported": ([_I, _I, _I, _I, _I, _I], _I),
+    "bqa_pack_weight_16_v2": ([_I, _I, _I, _I, _I, _P, _P, _P, _P], _I),
+    "bqa_to_point_major_16": ([_I, _I, _I, _I, _I, _P, _P, _P], _I),
+    "bqa_rows_to_16": ([_LL, _I, _I, _I, _I, _I, _P, _P, _P], _I),
+    "bqa_sa_mlp_max_v2_supported": ([_I, _I, _I, _I, _I, _I], _I),
+    "bqa_sa_mlp_max_forward_v2": ([_I, _I, _I, _I, _I, _P, _P, _P, _I, _P, _F, _I, _I, _I, _I,
+                                   _P, _P, _P, _P, _P, _P, _P, _I, _P], _I),
     "bqa_sa_mlp_max_forward_slice": ([_I, _I, _I, _I, _I, _I, _I, _P, _P, _P, _I, _P, _F, _I, _I, _I, _I,
                                       _P, _P, _P, _P, _P, _P, _P, _P, _I, _P], _I),
     "bqa_sa_mlp_max_forward": ([_I, _I, _I, _I, _I, _P, _P, _P, _I, _P, _F, _I, _I, _I, _I,

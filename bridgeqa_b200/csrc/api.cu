@@ -111,6 +111,19 @@ int sa_forward_dispatch(int b, int n, int npoint, int nsample, int c, const floa
                         float *out_cm, float *out_pm, int fp16, cudaStream_t stream, int npoint_total,
                         int j_offset);
 
+int sa_v2_supported(int nsample, int npoint, int c, int c1, int c2, int c3);
+int pack_weight_v2_dispatch(int c_out, int c_in, int kpad, int mode, int fp16, const float *w, const float *bias,
+                            void *packed, cudaStream_t stream);
+int to_point_major_16_dispatch(int b, int c, int n, int stride, int fp16, const float *in, void *out,
+                               cudaStream_t stream);
+int rows_to_16_dispatch(long long rows, int c, int row_stride, int first, int stride, int fp16, const float *in,
+                        void *out, cudaStream_t stream);
+int sa_v2_forward_dispatch(int b, int n, int npoint, int nsample, int c, const float *xyz, const float *new_xyz,
+                           const void *feat16, int stride16, const int *idx, float radius, int normalize_xyz,
+                           int c1, int c2, int c3, const void *w1p, const void *w2p, const void *w3p,
+                           const float *b3, float *out_cm, float *out_pm, void *out_pm16, int fp16,
+                           cudaStream_t stream);
+
 int fp_supported(int n, int m, int c_known, int c_skip, int c1, int c2);
 int fp_forward_dispatch(int b, int n, int m, int c_known, int c_skip, const float *unknown,
                         const float *known, const float *known_feat, int known_stride,
@@ -403,6 +416,66 @@ int bqa_sa_mlp_max_forward_slice(int b, int n, int npoint_total, int j_begin, in
   return sa_forward_dispatch(b, n, j_count, nsample, c, xyz, new_xyz, feat_pm, feat_stride, idx, radius,
                              normalize_xyz, c1, c2, c3, w1p, b1, w2p, b2, w3p, b3, out_cm, out_pm,
                              precision, (cudaStream_t)stream, npoint_total, j_begin);
+}
+
+int bqa_pack_weight_16_v2(int c_out, int c_in, int k_pad, int mode, int precision, const float *w,
+                          const float *bias, void *packed, void *stream) {
+  BQA_REQUIRE(precision == 0 || precision == 1, "%s: precision must be 0 (bf16) or 1 (fp16)", __func__);
+  BQA_REQUIRE(c_out > 0 && c_in > 0, "%s: empty weight", __func__);
+  BQA_REQUIRE(mode >= 0 && mode <= 2, "%s: mode must be 0, 1 or 2", __func__);
+  BQA_REQUIRE(k_pad % 16 == 0, "%s: k_pad=%d must be a multiple of 16", __func__, k_pad);
+  if (mode == 0) BQA_REQUIRE(k_pad >= c_in, "%s: k_pad=%d < c_in=%d", __func__, k_pad, c_in);
+  if (mode == 1) BQA_REQUIRE(c_in >= 3 && k_pad == (c_in - 3 + 5 + 15) / 16 * 16,
+                             "%s: mode 1 needs c_in >= 3 and k_pad = roundup16(c_in + 2)", __func__);
+  if (mode == 2) BQA_REQUIRE(k_pad == c_in + 16, "%s: mode 2 needs k_pad = c_in + 16", __func__);
+  PTR(w); PTR(packed);
+  return pack_weight_v2_dispatch(c_out, c_in, k_pad, mode, precision, w, bias, packed, (cudaStream_t)stream);
+}
+
+int bqa_to_point_major_16(int b, int c, int n, int stride, int precision, const float *in, void *out,
+                          void *stream) {
+  NONNEG(b); NONNEG(c); NONNEG(n);
+  BQA_REQUIRE(precision == 0 || precision == 1, "%s: precision must be 0 (bf16) or 1 (fp16)", __func__);
+  BQA_REQUIRE(stride >= c && stride % 8 == 0, "%s: stride=%d must be a multiple of 8 >= c=%d", __func__, stride, c);
+  if ((long long)b * c * n == 0) return BQA_OK;
+  BQA_REQUIRE(b <= 65535, "%s: batch too large", __func__);
+  PTR(in); PTR(out);
+  return to_point_major_16_dispatch(b, c, n, stride, precision, in, out, (cudaStream_t)stream);
+}
+
+int bqa_rows_to_16(long long rows, int c, int row_stride, int first, int stride, int precision,
+                   const float *in, void *out, void *stream) {
+  BQA_REQUIRE(rows >= 0 && c >= 0 && first >= 0, "%s: negative size", __func__);
+  BQA_REQUIRE(precision == 0 || precision == 1, "%s: precision must be 0 (bf16) or 1 (fp16)", __func__);
+  BQA_REQUIRE(row_stride >= first + c, "%s: row_stride=%d < first + c = %d", __func__, row_stride, first + c);
+  BQA_REQUIRE(stride >= c && stride % 8 == 0 && stride > 0, "%s: stride=%d must be a positive multiple of 8 >= c=%d",
+              __func__, stride, c);
+  if (rows == 0) return BQA_OK;
+  PTR(in); PTR(out);
+  return rows_to_16_dispatch(rows, c, row_stride, first, stride, precision, in, out, (cudaStream_t)stream);
+}
+
+int bqa_sa_mlp_max_v2_supported(int nsample, int npoint, int c, int c1, int c2, int c3) {
+  return sa_v2_supported(nsample, npoint, c, c1, c2, c3);
+}
+
+int bqa_sa_mlp_max_forward_v2(int b, int n, int npoint, int nsample, int c, const float *xyz,
+                              const float *new_xyz, const void *feat16, int stride16, const int *idx,
+                              float radius, int normalize_xyz, int c1, int c2, int c3, const void *w1p,
+                              const void *w2p, const void *w3p, const float *b3, float *out_cm,
+                              float *out_pm, void *out_pm16, int precision, void *stream) {
+  NONNEG(b); NONNEG(n); NONNEG(npoint); NONNEG(nsample); NONNEG(c);
+  BQA_REQUIRE(precision == 0 || precision == 1, "%s: precision must be 0 (bf16) or 1 (fp16)", __func__);
+  if ((long long)b * npoint == 0) return BQA_OK;
+  PTR(xyz); PTR(new_xyz); PTR(idx); PTR(w1p); PTR(w2p); PTR(w3p); PTR(b3); PTR(out_cm);
+  BQA_REQUIRE((c == 0) == (feat16 == nullptr), "%s: feat16 must be NULL iff c == 0", __func__);
+  BQA_REQUIRE(c == 0 || (stride16 % 8 == 0 && stride16 >= (c + 7) / 8 * 8),
+              "%s: stride16=%d must be a multiple of 8 >= roundup8(c=%d)", __func__, stride16, c);
+  BQA_REQUIRE(c == 0 || (reinterpret_cast<uintptr_t>(feat16) & 15) == 0, "%s: feat16 must be 16-byte aligned", __func__);
+  BQA_REQUIRE(!normalize_xyz || radius > 0.f, "%s: radius must be > 0", __func__);
+  return sa_v2_forward_dispatch(b, n, npoint, nsample, c, xyz, new_xyz, feat16, stride16, idx, radius,
+                                normalize_xyz, c1, c2, c3, w1p, w2p, w3p, b3, out_cm, out_pm, out_pm16,
+                                precision, (cudaStream_t)stream);
 }
 
 int bqa_fp_mlp_supported(int n, int m, int c_known, int c_skip, int c1, int c2) {

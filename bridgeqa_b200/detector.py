@@ -72,7 +72,9 @@ class Pointnet2Backbone(nn.Module):
             # when the channel count allows 16-byte loads (C % 4 == 0, e.g. the 132-d multiview
             # config) one packed copy makes the rows aligned (the view starts 12 bytes in)
             c = pc.size(-1) - 3
-            features._bqa_pm = pc[..., 3:].contiguous() if (c % 4 == 0 and c >= 16) else pc[..., 3:]
+            features._bqa_pm = pc[..., 3:].contiguous() if (c % 4 == 0 and c >= 16 and not fused.sa_v2_enabled()) \
+                else pc[..., 3:]
+            features._bqa_cloud = pc        # fused.point_major_16 converts the feature columns row-wise
         return xyz, features
 
     def _sample_lower_levels(self, xyz1):

@@ -9,6 +9,7 @@ kernel of the C ABI.
 """
 import contextlib
 import ctypes
+import os
 import threading
 
 import torch
@@ -111,6 +112,18 @@ class PackedSA(object):
             self.packed.append(img)
             self.bias.append(b)
         self.device = self.packed[0].device
+        # images of the warp-specialised kernel (sa_fused_v2.cu): biases of layers 1-2 folded into K
+        self.packed_v2 = []
+        folded = [pt_utils.fold_conv_bn(blk) for blk in mlp_module]
+        c = self.c_in - 3
+        for li, (w, b) in enumerate(folded):
+            c_out, c_in = w.shape
+            kpad = ((c + 5 + 15) // 16 * 16, c_in + 16, c_in)[li]
+            img = torch.empty(c_out * kpad, dtype=torch.int16, device=w.device)
+            with torch.cuda.device(w.device):
+                N.call("bqa_pack_weight_16_v2", c_out, c_in, kpad, (1, 2, 0)[li], self.precision, N.ptr(w),
+                       N.ptr(b.contiguous()), N.ptr(img), N.stream_ptr(w.device))
+            self.packed_v2.append(img)
 
 
 def weights_signature(module):
@@ -161,6 +174,41 @@ def point_major(features):
             and pm.stride(0) == pm.size(1) * pm.stride(1)):
         return pm
     return _ext.transpose_to_point_major(features.contiguous())
+
+
+def point_major_16(features):
+    """(B,C,N) channel-major features -> ((B,N,stride) 16-bit point-major tensor in the current
+    operand precision, rows zero padded to `stride` = roundup8(C)).  Fused SA layers attach the twin
+    they wrote (`_bqa_pm16`); the backbone's input features carry the (B,N,3+C) cloud they are a view
+    of (`_bqa_cloud`), which is converted row-wise without a transpose; anything else goes through
+    one transpose-convert kernel."""
+    prec = _PRECISIONS[_state["precision"]]
+    pm = getattr(features, "_bqa_pm16", None)
+    if (pm is not None and getattr(features, "_bqa_pm16_prec", None) == prec and pm.device == features.device
+            and pm.dim() == 3 and pm.size(0) == features.size(0) and pm.size(1) == features.size(2)
+            and pm.size(2) >= features.size(1) and pm.is_contiguous()):
+        return pm
+    b, c, n = features.shape
+    stride = (c + 7) // 8 * 8
+    out = torch.empty((b, n, stride), dtype=torch.int16, device=features.device)
+    cloud = getattr(features, "_bqa_cloud", None)
+    with torch.cuda.device(features.device):
+        if (cloud is not None and cloud.is_contiguous() and cloud.dtype == _f32 and cloud.device == features.device
+                and cloud.dim() == 3 and cloud.size(0) == b and cloud.size(1) == n and cloud.size(2) == c + 3):
+            N.call("bqa_rows_to_16", ctypes.c_longlong(b * n), c, c + 3, 3, stride, prec, N.ptr(cloud), N.ptr(out),
+                   N.stream_ptr(features.device))
+        else:
+            f = features.contiguous()
+            N.check_tensor(f, "features", _f32)
+            N.call("bqa_to_point_major_16", b, c, n, stride, prec, N.ptr(f), N.ptr(out),
+                   N.stream_ptr(features.device))
+    return out
+
+
+def sa_v2_enabled():
+    """The warp-specialised SA kernel (sa_fused_v2.cu) is the default; BQA_SA_V2=0 selects the
+    round-1 kernel (sa_fused.cu) for A/B measurements."""
+    return os.environ.get("BQA_SA_V2", "1") != "0"
 
 
 GRID_MIN_POINTS = 256      # prebuilt grids: below this a scan is as fast as the search
@@ -264,9 +312,10 @@ def ball_query_on_grid(new_xyz, xyz, radius, nsample, grid):
     return idx
 
 
-def sa_forward(xyz, new_xyz, features, radius, nsample, normalize_xyz, packed, grid=None):
-    """-> new_features (B, C3, npoint) fp32, with a point-major twin attached as ._bqa_pm.
-    `grid`: optional (buffer, event) from prebuild_ball_query_grid(xyz, ...)."""
+def sa_forward(xyz, new_xyz, features, radius, nsample, normalize_xyz, packed, grid=None, pm32=True):
+    """-> new_features (B, C3, npoint) fp32, with point-major twins attached: ._bqa_pm16 (16-bit, what
+    the next fused SA layer gathers from) and, when pm32, ._bqa_pm (fp32, what the fused FP layers
+    interpolate from).  `grid`: optional (buffer, event) from prebuild_ball_query_grid(xyz, ...)."""
     N.check_tensor(xyz, "xyz", _f32)
     N.check_tensor(new_xyz, "new_xyz", _f32)
     b, n, _ = xyz.shape
@@ -275,12 +324,28 @@ def sa_forward(xyz, new_xyz, features, radius, nsample, normalize_xyz, packed, g
         idx = ball_query_on_grid(new_xyz, xyz, radius, nsample, grid)
     else:
         idx = _ext.ball_query(new_xyz, xyz, radius, nsample)
+    c = features.size(1) if features is not None else 0
+    out_cm = torch.empty((b, packed.c3, npoint), dtype=_f32, device=xyz.device)
+    if sa_v2_enabled() and N.lib().bqa_sa_mlp_max_v2_supported(int(nsample), npoint, c, packed.c1, packed.c2,
+                                                               packed.c3):
+        pm16 = point_major_16(features) if features is not None else None
+        out_pm = torch.empty((b, npoint, packed.c3), dtype=_f32, device=xyz.device) if pm32 else None
+        out_pm16 = torch.empty((b, npoint, packed.c3), dtype=torch.int16, device=xyz.device)
+        with torch.cuda.device(xyz.device):
+            N.call("bqa_sa_mlp_max_forward_v2", b, n, npoint, int(nsample), c, N.ptr(xyz), N.ptr(new_xyz),
+                   N.ptr(pm16), pm16.size(2) if pm16 is not None else 0, N.ptr(idx), ctypes.c_float(radius),
+                   1 if normalize_xyz else 0, packed.c1, packed.c2, packed.c3, N.ptr(packed.packed_v2[0]),
+                   N.ptr(packed.packed_v2[1]), N.ptr(packed.packed_v2[2]), N.ptr(packed.bias[2]),
+                   N.ptr(out_cm), N.ptr(out_pm), N.ptr(out_pm16), packed.precision, N.stream_ptr(xyz.device))
+        if out_pm is not None:
+            out_cm._bqa_pm = out_pm
+        out_cm._bqa_pm16, out_cm._bqa_pm16_prec = out_pm16, packed.precision
+        return out_cm
     if features is not None:
         pm = point_major(features)
         c, stride = pm.size(2), pm.stride(1)
     else:
         pm, c, stride = None, 0, 0
-    out_cm = torch.empty((b, packed.c3, npoint), dtype=_f32, device=xyz.device)
     out_pm = torch.empty((b, npoint, packed.c3), dtype=_f32, device=xyz.device)
     with torch.cuda.device(xyz.device):
         N.call("bqa_sa_mlp_max_forward", b, n, npoint, int(nsample), c, N.ptr(xyz), N.ptr(new_xyz),

@@ -228,6 +228,44 @@ BQA_API int bqa_sa_mlp_max_forward_slice(int b, int n, int npoint_total, int j_b
                                          const float *b2, const void *w3p, const float *b3,
                                          float *out_cm, float *out_pm, int precision, void *stream);
 
+/* ---- fused set-abstraction layer, warp-specialised form (csrc/sa_fused_v2.cu) ------------------
+ * Same contract and arithmetic class as bqa_sa_mlp_max_forward (same reference lines:
+ * pointnet2_utils.py:317-376 + pytorch_utils.py:11-36 + pointnet2_modules.py:259-262), different
+ * execution: producer / MMA-issuer / epilogue warps of one persistent CTA work on up to four tiles
+ * in flight, features are gathered from a 16-BIT point-major copy with cp.async, biases are folded
+ * into the tensor-core contraction.
+ *
+ * bqa_pack_weight_16_v2: w (c_out, c_in) f32 (BN folded), bias (c_out) f32 or NULL -> 16-bit image
+ *   [k_pad/8][c_out][8].  mode 0: plain, k_pad >= c_in (layer 3; bias is passed to the kernel as
+ *   f32).  mode 1: layer 1 of an SA block, source columns [xyz(3), feat(c)] (c = c_in - 3), k_pad =
+ *   roundup16(c + 5): feature f at K = f, xyz at K = kx..kx+2 with kx = max(c, k_pad - 16), the
+ *   bias as two 16-bit halves (hi + lo) at kx+3, kx+4.  mode 2: layer 2, k_pad = c_in + 16, bias
+ *   halves at K = c_in, c_in + 1.
+ * bqa_to_point_major_16: (b, c, n) f32 channel-major -> (b, n, stride) 16-bit point-major, zero
+ *   padded from c to stride (stride a multiple of 8, >= c).
+ * bqa_rows_to_16: rows x [first, first + c) of an f32 matrix with row_stride floats per row (the
+ *   (b*n, 3 + C) input cloud: first = 3) -> (rows, stride) 16-bit, zero padded.
+ * bqa_sa_mlp_max_v2_supported: nsample in {16,32,64} (128 for the (64,64,128) widths), npoint a
+ *   multiple of 128/nsample, widths (64,64,128) | (128,128,256) | (128,128,128), c <= 1024.
+ * bqa_sa_mlp_max_forward_v2: feat16 (b, n, stride16) 16-bit point-major in `precision`'s format
+ *   (NULL iff c == 0; stride16 a multiple of 8 and >= roundup8(c), rows zero padded, 16-byte
+ *   aligned); w1p / w2p / w3p from bqa_pack_weight_16_v2 modes 1 / 2 / 0; b3 f32.  Outputs:
+ *   out_cm (b,c3,npoint) f32; optional out_pm (b,npoint,c3) f32 and out_pm16 (b,npoint,c3) 16-bit
+ *   point-major copies for the next layer. */
+BQA_API int bqa_pack_weight_16_v2(int c_out, int c_in, int k_pad, int mode, int precision,
+                                  const float *w, const float *bias, void *packed, void *stream);
+BQA_API int bqa_to_point_major_16(int b, int c, int n, int stride, int precision, const float *in,
+                                  void *out, void *stream);
+BQA_API int bqa_rows_to_16(long long rows, int c, int row_stride, int first, int stride, int precision,
+                           const float *in, void *out, void *stream);
+BQA_API int bqa_sa_mlp_max_v2_supported(int nsample, int npoint, int c, int c1, int c2, int c3);
+BQA_API int bqa_sa_mlp_max_forward_v2(int b, int n, int npoint, int nsample, int c, const float *xyz,
+                                      const float *new_xyz, const void *feat16, int stride16,
+                                      const int *idx, float radius, int normalize_xyz, int c1, int c2,
+                                      int c3, const void *w1p, const void *w2p, const void *w3p,
+                                      const float *b3, float *out_cm, float *out_pm, void *out_pm16,
+                                      int precision, void *stream);
+
 /* ---- fused feature-propagation layer (inference) -----------------------------------
  * replaces PointnetFPModule.forward (pointnet2_modules.py:376-421): three_nn ->
  * 1/(dist+1e-8) weights normalised over the 3 neighbours -> three_interpolate -> cat with
