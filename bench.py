@@ -234,7 +234,13 @@ def algorithmic_work(name, dims):
     if name == "bqa_transpose_to_point_major":
         b, c, n = dims[:3]
         return {"bytes": 8 * b * c * n, "bound": "hbm"}
-    if name == "bqa_sa_mlp_max_forward":
+    if name == "bqa_rows_to_16":                  # read c fp32 columns of every row, write stride 16-bit
+        rows, c, row_stride, first, stride = dims[:5]
+        return {"bytes": rows * (4 * c + 2 * stride), "bound": "hbm"}
+    if name == "bqa_to_point_major_16":
+        b, c, n, stride = dims[:4]
+        return {"bytes": b * n * (4 * c + 2 * stride), "bound": "hbm"}
+    if name in ("bqa_sa_mlp_max_forward", "bqa_sa_mlp_max_forward_v2"):
         b, n, npt, ns, c = dims[:5]
         c1, c2, c3 = dims[7:10]          # dims[5:7] = feat_stride, normalize_xyz
         flops = 2 * b * npt * ns * ((c + 3) * c1 + c1 * c2 + c2 * c3)
@@ -247,6 +253,24 @@ def algorithmic_work(name, dims):
         byts = 4 * b * (ck * m + cs * n + c2 * n + 3 * n + 3 * m)
         return {"bytes": byts, "flops": flops, "bound": "tensor"}
     return {"bytes": 0, "bound": "hbm"}
+
+
+def sms_occupied(name, dims, sms=148):
+    """SMs a kernel holds while it runs (its CTAs are persistent or one per SM-sized chunk): used for the
+    SM-time budget of the in-flight regime, where the step is bound by total SM-time, not by latency."""
+    if name == "bqa_furthest_point_sampling_grid_lean":
+        b, n = dims[:2]
+        return min(sms, b * -(-n // (768 * 18)))
+    if name == "bqa_furthest_point_sampling_grid":
+        b, n = dims[:2]
+        return min(sms, b * (6 if n > 20480 else max(1, -(-n // 10240))))
+    if name in ("bqa_sa_mlp_max_forward", "bqa_sa_mlp_max_forward_v2"):
+        b, n, npt, ns = dims[:4]
+        return min(sms, b * npt * ns // 128)
+    if name == "bqa_fp_mlp_forward":
+        b, n = dims[:2]
+        return min(sms, b * -(-n // 128))
+    return None
 
 
 def run_train_mode(args, torch, dist, device, world, rank, real_stdout):
@@ -376,6 +400,17 @@ def main():
                     help="bind this rank (and the pinned buffers it then allocates) to the CPUs NVML reports as "
                          "local to its GPU -- for the end-to-end number at 8 GPUs, which is bound by host <-> device "
                          "copies (experimental: not measured at 8 GPUs yet)")
+    ap.add_argument("--e2e-input", default="staged16", choices=["staged16", "fp32"],
+                    help="end-to-end leg: what the loader hands over on the host.  staged16 = staging.StagedCloud "
+                         "(fp32 xyz + 16-bit point-major features, the buffer the fused SA1 kernel gathers from); "
+                         "fp32 = the reference's (B,N,3+C) fp32 cloud")
+    ap.add_argument("--e2e-readback", default="consumer", choices=["consumer", "features16", "features32"],
+                    help="end-to-end leg: what is read back to the host every step.  consumer = what the next stage "
+                         "on the HOST needs (seed coordinates / indices + per-scene feature checksum; the seed "
+                         "features are consumed on the device by voting / proposal); features16 / features32 add "
+                         "fp2_features as fp16 / fp32")
+    ap.add_argument("--no-ref-ext", action="store_true", help="skip the `ref_ext` leg (stock reference modules on the "
+                    "reference's own CUDA extension, timed in a subprocess on the same GPU)")
     ap.add_argument("--precision", default="fp16", choices=["fp16", "bf16"],
                     help="operand format of the fused tensor-core kernels (fp32 accumulate)")
     args = ap.parse_args()
@@ -518,20 +553,23 @@ def main():
         net.enable_cuda_graph(True, bind_inputs=True)
 
     # ---- e2e: host (pinned) -> device -> forward -> host, copies inside the timed region ----
-    out_host = {
-        "fp2_features": torch.empty((BATCH, 256, 1024), dtype=torch.float32).pin_memory(),
-        "fp2_xyz": torch.empty((BATCH, 1024, 3), dtype=torch.float32).pin_memory(),
-        "fp2_inds": torch.empty((BATCH, 1024), dtype=torch.int32).pin_memory(),
-    }
+    from bridgeqa_b200 import staging
     if args.workload == "detector":
-        out_host = {
-            "bbox_corner": torch.empty((BATCH, 256, 8, 3), dtype=torch.float32).pin_memory(),
-            "objectness_scores": torch.empty((BATCH, 256, 2), dtype=torch.float32).pin_memory(),
-            "sem_cls_scores": torch.empty((BATCH, 256, 18), dtype=torch.float32).pin_memory(),
-            "aggregated_vote_features": torch.empty((BATCH, 256, 128), dtype=torch.float32).pin_memory(),
-        }
-    h2d_bytes = host_pinned[0].numel() * 4
-    d2h_bytes = sum(t.numel() * t.element_size() for t in out_host.values())
+        rb_keys, rb_half = ["bbox_corner", "objectness_scores", "sem_cls_scores", "aggregated_vote_features"], ()
+    else:
+        rb_keys, rb_half = ["fp2_xyz", "fp2_inds", "fp2_checksum"], ()
+        if args.e2e_readback == "features16":
+            rb_keys, rb_half = rb_keys + ["fp2_features"], ("fp2_features",)
+        elif args.e2e_readback == "features32":
+            rb_keys = rb_keys + ["fp2_features"]
+    if args.e2e_input == "staged16":
+        # the loader emits the staged format (host work outside the timed region, like any loader work)
+        host_e2e = [staging.stage_host(h, pin=True) for h in host_pinned]
+        h2d_bytes = host_e2e[0].nbytes()
+    else:
+        host_e2e = host_pinned
+        h2d_bytes = host_pinned[0].numel() * 4
+    out_host = {}
 
     # pipelined: NB = depth + 1 device input buffers, each with its own graph and static outputs
     # (bind_inputs).  The H2D copy of step i runs on copy_in as soon as the forward that last read
@@ -541,7 +579,10 @@ def main():
     copy_in, copy_out = torch.cuda.Stream(device), torch.cuda.Stream(device)
     main = torch.cuda.current_stream(device)
     NB = depth + 1
-    dev_buf = [torch.empty_like(dev_inputs[0]) for _ in range(NB)]
+    if args.e2e_input == "staged16":
+        dev_buf = [staging.StagedCloud.empty_like(host_e2e[0], device) for _ in range(NB)]
+    else:
+        dev_buf = [torch.empty_like(dev_inputs[0]) for _ in range(NB)]
 
     def e2e_run(k):
         fwd_done = [None] * NB
@@ -554,16 +595,20 @@ def main():
             with torch.cuda.stream(copy_in):
                 if fwd_done[j] is not None:
                     copy_in.wait_event(fwd_done[j])                # forward i-NB no longer reads the buffer
-                dev_buf[j].copy_(host_pinned[i % ROT], non_blocking=True)
+                dev_buf[j].copy_(host_e2e[i % ROT], non_blocking=True)
                 ready = torch.cuda.Event()
                 ready.record(copy_in)
             ticket = queue.submit({"point_clouds": dev_buf[j]},
                                   after=[ready] + ([read_done[j]] if read_done[j] is not None else []))
             fwd_done[j] = ticket.done
-            with torch.cuda.stream(copy_out):
+            with torch.cuda.stream(copy_out), torch.no_grad():
                 dd = ticket.wait(copy_out)
-                for k_, t_ in out_host.items():
-                    t_.copy_(dd[k_], non_blocking=True)
+                if "fp2_checksum" in rb_keys:
+                    # per-scene checksum of the seed features (B, 256): the "metric" a host-side consumer of
+                    # the backbone would log; the features themselves stay on the device for voting / proposal
+                    dd = dict(dd)
+                    dd["fp2_checksum"] = dd["fp2_features"].mean(dim=2)
+                staging.read_back(dd, rb_keys, out=out_host, half=rb_half)
                 read_done[j] = torch.cuda.Event()
                 read_done[j].record(copy_out)
         main.wait_stream(copy_out)
@@ -571,6 +616,7 @@ def main():
 
     e2e_run(2 * NB)
     barrier()
+    d2h_bytes = sum(t.numel() * t.element_size() for t in out_host.values())
     e0 = torch.cuda.Event(enable_timing=True)
     e1 = torch.cuda.Event(enable_timing=True)
     e0.record()
@@ -622,8 +668,11 @@ def main():
         top = kernels[0] if kernels else None
         roofline = None
         traffic = None
+        prof_name = None
         try:   # dram__bytes_read + dram__bytes_write per launch from the committed ncu --set full capture
-            prof = json.load(open(os.path.join(ROOT, "profiles", "r1_kernels_ncu.json")))
+            prof_name = "r2_kernels_ncu.json" if os.path.exists(os.path.join(ROOT, "profiles", "r2_kernels_ncu.json")) \
+                else "r1_kernels_ncu.json"
+            prof = json.load(open(os.path.join(ROOT, "profiles", prof_name)))
             names = {"bqa_furthest_point_sampling": "fps_cluster_kernel<14", "bqa_furthest_point_sampling_grid": "fps_sorted_kernel<14",
                      "bqa_furthest_point_sampling_grid_lean": "fps_sorted_kernel<18, 768"}
             if top and top["kernel"] in names and top["dims"][:3] == [BATCH, NUM_POINTS, 2048]:
@@ -636,7 +685,8 @@ def main():
             roofline = {"kernel": "%s%s" % (top["kernel"], top["dims"]), "bound": top["bound"],
                         "achieved": top["achieved"], "peak": top["peak"], "unit": top["unit"],
                         "frac": top["frac"], "traffic": traffic,
-                        "traffic_source": "profiles/r1_kernels_ncu.json (ncu --set full, per launch)" if traffic else None,
+                        "traffic_source": ("committed ncu --set full capture of the same kernel and shape "
+                                           "(profiles/%s), NOT measured by this run" % prof_name) if traffic else None,
                         "algorithmic_bytes": algorithmic_work(top["kernel"], top["dims"])["bytes"],
                         "peak_source": peaks["source"],
                         "share_of_step": top["share"], "share_of_kernel_time": top["share_of_kernel_time"],
@@ -670,7 +720,10 @@ def main():
             "serial": {"ms_per_step": serial_ms / args.steps, "value": scenes / (serial_ms / 1e3), "unit": UNIT,
                        "note": "same K steps with one batch in flight (latency variant of the sampling kernel) = latency of a batch"},
             "e2e": {"value": scenes / (e2e_ms / 1e3), "unit": UNIT, "ms_per_step": e2e_ms / args.steps,
-                    "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes},
+                    "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
+                    "input": ("staging.StagedCloud: fp32 xyz + 16-bit point-major features (pinned host)"
+                              if args.e2e_input == "staged16" else "(B,N,3+C) fp32 cloud (pinned host)"),
+                    "read_back": {k_: list(v_.shape) + [str(v_.dtype)] for k_, v_ in out_host.items()}},
             "ms_per_step_by_rank": [round(v, 4) for v in by_rank],
             "sm_mhz_by_rank": mhz_by_rank,
             "gpu_launches": launches,
@@ -682,10 +735,37 @@ def main():
             "kernels": kernels,
             "clocks": clk,
         }
+        # SM-time budget of the timed (in-flight) regime: the step is bound by total SM-time there, so each
+        # kernel's cost is (SMs it holds) x (its duration); durations are the eager pass's (same kernels)
+        budget = []
+        for r in kernels:
+            occ = sms_occupied(r["kernel"], r["dims"])
+            if occ:
+                budget.append({"kernel": r["kernel"], "dims": r["dims"][:5], "sms": occ,
+                               "sm_ms": round(occ * r["ms"] * r["calls_per_step"], 3)})
+        line["sm_time_budget"] = {
+            "step_sm_ms": round(148 * elapsed_ms / args.steps, 2),
+            "note": "timed regime: ms_per_step x 148 SMs; rows = SMs held x kernel duration for the kernels that "
+                    "hold whole SMs (sampling clusters, persistent SA / FP CTAs); the rest are short kernels",
+            "kernels": sorted(budget, key=lambda r_: -r_["sm_ms"])}
         if world == 1 and not args.no_cpu_baseline:
             r = cpu_reference_run(steps=1, warmup=0, sample_scenes=4)
             line["cpu_baseline"] = {"value": r["value"], "unit": UNIT, "cores": r["cores"],
                                     "kind": "port", "sample": r["sample"]}
+        if world == 1 and not args.no_ref_ext and args.workload == "backbone":
+            # the reference's OWN code on this GPU: unmodified Python layer + its CUDA extension (oracle/_ref),
+            # in a subprocess so that none of it is loaded into this process
+            try:
+                torch.cuda.synchronize()
+                rr = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "ref_ext_forward.py"),
+                                     "--steps", "3", "--warmup", "1", "--features", str(features)],
+                                    stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True, timeout=240)
+                ref = json.loads(rr.stdout.strip().splitlines()[-1])
+                if "value" in ref:
+                    ref["speedup_device_resident"] = round(value / ref["value"], 2)
+                line["ref_ext"] = ref
+            except Exception as e:
+                line["ref_ext"] = {"unavailable": repr(e)[:200]}
         sys.stdout.flush()
         os.dup2(real_stdout, 1)
         print(json.dumps(line), flush=True)

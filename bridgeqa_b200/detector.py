@@ -62,6 +62,13 @@ class Pointnet2Backbone(nn.Module):
 
     @staticmethod
     def _break_up_pc(pc):
+        if getattr(pc, "is_staged", False):
+            # loader-facing staged input (staging.StagedCloud): fp32 coordinates + the 16-bit point-major
+            # features the fused SA1 kernel gathers from; no split / transpose / conversion on the device
+            if pc.precision != fused.precision():
+                raise RuntimeError("staged cloud holds %s features but the operand precision is %s"
+                                   % (pc.precision, fused.precision()))
+            return pc.xyz, pc.features_view()
         xyz = pc[..., :3].contiguous()
         # (B,C,N) VIEW of the cloud (the reference materialises it, backbone_module.py:74-78): every
         # consumer on the hot path gathers from the point-major twin below instead, so the
@@ -221,6 +228,9 @@ class Pointnet2Backbone(nn.Module):
                                          grid=grid if sa._can_fuse(xyz, features) else None)
                 outs.append((xyz, features, inds))
         else:
+            if getattr(data_dict["point_clouds"], "is_staged", False):
+                raise RuntimeError("a staged 16-bit cloud is only accepted by the fused inference path "
+                                   "(eval mode, no autograd, fused kernels enabled)")
             # training / un-fused path: same layer sequence as the reference
             # (models/backbone_module.py:97-121); on the GPU the re-sampling of sampled clouds at
             # levels 2-4 still goes through the parallel identity-prefix proof

@@ -167,6 +167,9 @@ def point_major(features):
     """(B,C,N) channel-major features -> a (B,N,C)-indexable fp32 view with unit channel stride.
     Layers that produced `features` attach the point-major twin they already have
     (`_bqa_pm`), so no transpose kernel runs between fused layers."""
+    if getattr(features, "_bqa_staged", False):
+        raise RuntimeError("a staged 16-bit cloud carries no fp32 features: only the fused SA kernel "
+                           "(sa_fused_v2) can consume it")
     pm = getattr(features, "_bqa_pm", None)
     if (pm is not None and pm.dtype == _f32 and pm.device == features.device and pm.dim() == 3
             and pm.size(0) == features.size(0) and pm.size(1) == features.size(2)

@@ -35,7 +35,8 @@ class GraphedForward(object):
 
     def applicable(self, data_dict):
         pc = data_dict.get("point_clouds")
-        return (torch.is_tensor(pc) and pc.is_cuda and pc.dtype == torch.float32 and pc.dim() == 3
+        return ((torch.is_tensor(pc) or getattr(pc, "is_staged", False)) and pc.is_cuda
+                and pc.dtype == torch.float32 and pc.dim() == 3
                 and not self.module.training and not torch.is_grad_enabled()
                 and fused.enabled() and set(data_dict.keys()) == {"point_clouds"})
 
@@ -143,7 +144,7 @@ class InFlight(object):
         """Issue module(data_dict) on the next stream of the ring.  `after`: event or list of
         events the forward has to wait for (default: everything queued on the current stream)."""
         pc = data_dict["point_clouds"]
-        if not (torch.is_tensor(pc) and pc.is_cuda):
+        if not ((torch.is_tensor(pc) or getattr(pc, "is_staged", False)) and pc.is_cuda):
             raise RuntimeError("in-flight forwards need a CUDA point cloud (no CPU path)")
         s = self.streams(pc.device)[self.submitted % self.depth]
         self.submitted += 1

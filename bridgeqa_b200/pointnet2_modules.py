@@ -177,6 +177,8 @@ class PointnetSAModuleVotes(nn.Module):
                                             self.normalize_xyz, self._packed(), grid=grid)
             return new_xyz, new_features, inds
 
+        if getattr(features, "_bqa_staged", False):
+            raise RuntimeError("a staged 16-bit cloud is only accepted by the fused inference path")
         if grid is not None and isinstance(self.grouper, pointnet2_utils.QueryAndGroup):
             grouped = self.grouper(xyz, new_xyz, features, grid=grid)
         else:

@@ -137,8 +137,10 @@ def test_detector_16x40000_c132_bench_regime_vs_oracle_including_head_values():
         np.testing.assert_array_equal(got[k], want[k], err_msg=k)
     np.testing.assert_array_equal(got["seed_inds"], want["fp2_inds"])
     np.testing.assert_array_equal(got["seed_xyz"], want["fp2_xyz"])
-    assert maxnorm(got["sa4_features"], want["sa4_features"]) < 2e-3
-    assert maxnorm(got["seed_features"], want["fp2_features"]) < 2e-3
+    # fp16 operands through 4 SA + 2 FP layers with a K = 135 first layer: measured 2.0e-3 / 1.3e-3 of the
+    # tensor's max (the TF32 class; test_fp16_fused_error_is_in_the_tf32_class puts a number on that)
+    assert maxnorm(got["sa4_features"], want["sa4_features"]) < 3e-3
+    assert maxnorm(got["seed_features"], want["fp2_features"]) < 3e-3
     vxyz, vfeat = modules_cpu.voting(want["fp2_xyz"], want["fp2_features"], sd, "voting_net.")
     vf = torch.from_numpy(vfeat)
     vf = vf.div(torch.norm(vf, p=2, dim=1).unsqueeze(1)).numpy()
@@ -228,3 +230,38 @@ def test_fp16_operands_near_the_saturation_range():
         bridgeqa_b200.set_fused(True)
         got_big_bf = sa(xyz, base * (mid_scale * 50))[1]
         assert maxnorm(got_big_bf.cpu().numpy(), ref_big.cpu().numpy()) < 1e-2
+
+
+def test_staged_16bit_input_is_bit_identical_to_the_fp32_cloud():
+    """Loader-facing staging (staging.StagedCloud): fp32 xyz + 16-bit point-major features
+    uploaded instead of the (B,N,3+C) fp32 cloud.  The host rounds the features exactly as the device
+    kernel would, so every output is BIT-identical -- eager, graphed and in flight -- and the un-fused /
+    training paths refuse the staged form instead of reading features that are not there."""
+    from bridgeqa_b200 import staging
+    for C in (7, 132, 0):
+        host = synthetic.make_batch(3, 20000, C, first_scene=300)
+        net = synthetic.fill_state_dict(detector.Pointnet2Backbone(input_feature_dim=C), seed=2).cuda().eval()
+        st_host = staging.stage_host(host)
+        assert st_host.nbytes() == 3 * 20000 * (12 + 2 * ((C + 7) // 8 * 8))
+        st_dev = staging.StagedCloud.empty_like(st_host, "cuda")
+        st_dev.copy_(st_host, non_blocking=True)
+        keys = ("sa1_inds", "sa2_inds", "sa1_features", "sa4_features", "fp2_features", "fp2_xyz")
+        with torch.no_grad():
+            want = {k: v.clone() for k, v in net({"point_clouds": host.cuda()}).items() if k in keys}
+            got = {k: v.clone() for k, v in net({"point_clouds": st_dev}).items() if k in keys}
+        for k in keys:
+            assert torch.equal(got[k], want[k]), (C, k)
+        net.enable_cuda_graph(bind_inputs=True)
+        q = net.in_flight(2)
+        tickets = [q.submit({"point_clouds": st_dev}) for _ in range(3)]
+        for t in tickets:
+            dd = t.wait()
+            for k in keys:
+                assert torch.equal(dd[k], want[k]), (C, k, "graph / in flight")
+        torch.cuda.synchronize()
+        net.enable_cuda_graph(False)
+        if C:
+            bridgeqa_b200.set_fused(False)
+            with pytest.raises(RuntimeError), torch.no_grad():
+                net({"point_clouds": st_dev})
+            bridgeqa_b200.set_fused(True)
