@@ -68,8 +68,6 @@ _SIGNATURES = {
     "bqa_sa_mlp_max_v2_supported": ([_I, _I, _I, _I, _I, _I], _I),
     "bqa_sa_mlp_max_forward_v2": ([_I, _I, _I, _I, _I, _P, _P, _P, _I, _P, _F, _I, _I, _I, _I,
                                    _P, _P, _P, _P, _P, _P, _P, _I, _P], _I),
-    "bqa_sa_mlp_max_forward_slice": ([_I, _I, _I, _I, _I, _I, _I, _P, _P, _P, _I, _P, _F, _I, _I, _I, _I,
-                                      _P, _P, _P, _P, _P, _P, _P, _P, _I, _P], _I),
     "bqa_sa_mlp_max_forward": ([_I, _I, _I, _I, _I, _P, _P, _P, _I, _P, _F, _I, _I, _I, _I,
                                 _P, _P, _P, _P, _P, _P, _P, _P, _I, _P], _I),
 }

@@ -398,26 +398,6 @@ int bqa_sa_mlp_max_forward(int b, int n, int npoint, int nsample, int c, const f
                              precision, (cudaStream_t)stream, npoint, 0);
 }
 
-int bqa_sa_mlp_max_forward_slice(int b, int n, int npoint_total, int j_begin, int j_count, int nsample,
-                                 int c, const float *xyz, const float *new_xyz, const float *feat_pm,
-                                 int feat_stride, const int *idx, float radius, int normalize_xyz,
-                                 int c1, int c2, int c3, const void *w1p, const float *b1,
-                                 const void *w2p, const float *b2, const void *w3p, const float *b3,
-                                 float *out_cm, float *out_pm, int precision, void *stream) {
-  NONNEG(b); NONNEG(n); NONNEG(npoint_total); NONNEG(nsample); NONNEG(c);
-  BQA_REQUIRE(j_begin >= 0 && j_count >= 0 && j_begin + j_count <= npoint_total,
-              "%s: slice [%d, %d) outside [0, %d)", __func__, j_begin, j_begin + j_count, npoint_total);
-  if ((long long)b * j_count == 0) return BQA_OK;
-  BQA_REQUIRE(precision == 0 || precision == 1, "%s: precision must be 0 (bf16) or 1 (fp16)", __func__);
-  PTR(xyz); PTR(new_xyz); PTR(idx); PTR(w1p); PTR(b1); PTR(w2p); PTR(b2); PTR(w3p); PTR(b3); PTR(out_cm);
-  BQA_REQUIRE((c == 0) == (feat_pm == nullptr), "%s: feat_pm must be NULL iff c == 0", __func__);
-  BQA_REQUIRE(c == 0 || feat_stride >= c, "%s: feat_stride=%d < c=%d", __func__, feat_stride, c);
-  BQA_REQUIRE(!normalize_xyz || radius > 0.f, "%s: radius must be > 0", __func__);
-  return sa_forward_dispatch(b, n, j_count, nsample, c, xyz, new_xyz, feat_pm, feat_stride, idx, radius,
-                             normalize_xyz, c1, c2, c3, w1p, b1, w2p, b2, w3p, b3, out_cm, out_pm,
-                             precision, (cudaStream_t)stream, npoint_total, j_begin);
-}
-
 int bqa_pack_weight_16_v2(int c_out, int c_in, int k_pad, int mode, int precision, const float *w,
                           const float *bias, void *packed, void *stream) {
   BQA_REQUIRE(precision == 0 || precision == 1, "%s: precision must be 0 (bf16) or 1 (fp16)", __func__);

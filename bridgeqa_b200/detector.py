@@ -47,11 +47,7 @@ class Pointnet2Backbone(nn.Module):
                 npoint=npoint, radius=radius, nsample=nsample, mlp=spec, use_xyz=True,
                 normalize_xyz=True))
         c = 256 * width
-        # FPS slices of SA1 whose ball query + MLP are pipelined underneath (1 = off, the default:
-        # measured slower on B200) -- developer knobs
         import os
-        self.sa1_slices = int(os.environ.get("BQA_SA1_SLICES", "1"))
-        self.sa1_exclusive = os.environ.get("BQA_FPS_EXCLUSIVE", "1") != "0"
         self.prefix_check = os.environ.get("BQA_FPS_PREFIX_CHECK", "1") != "0"
         # sampling over the cell-sorted points with warp-level pruning (fps_sorted.cu): bit-identical;
         # at 16 x 40000 the kernel is 7 % faster (1.60 -> 1.48 ms) but has to wait for the grid
@@ -191,35 +187,23 @@ class Pointnet2Backbone(nn.Module):
         if overlap:
             self._prefetched = None        # a prefetch is only ever consumed by the training branch
             main = torch.cuda.current_stream(xyz.device)
-            # SA1: sampling slices on this stream, their ball query + MLP underneath on a side
-            # stream; levels 2-4 are sampled on a second side stream as soon as SA1's centres exist
-            piped = (self.sa1.forward_pipelined(xyz, features, slices=self.sa1_slices,
-                                                exclusive=self.sa1_exclusive)
-                     if self.sa1_slices > 1 else None)
-            if piped is not None:
-                xyz1, feats1, inds1, done1 = piped
+            # SA1's cell grid serves both the sampling (pruned FPS over the cell-sorted points) and
+            # the ball query; without the sorted sampling it is built on a side stream underneath
+            # FPS1.  Levels 2-4 are sampled on a second side stream as soon as SA1's centres exist.
+            grid1 = None
+            if self.sa1._can_fuse(xyz, features):
+                sorted_fps = self.fps_grid and fused.fps_grid_supported(xyz.size(1), self.sa1.npoint)
+                grid1 = fused.prebuild_ball_query_grid(xyz, self.sa1.radius, inline=sorted_fps)
+            if grid1 is not None and grid1[1] is None:
+                inds1, xyz1 = fused.furthest_point_sample_grid(xyz, self.sa1.npoint, grid1)
             else:
-                # SA1's cell grid serves both the sampling (pruned FPS over the cell-sorted
-                # points) and the ball query; without the sorted sampling it is built on a side
-                # stream underneath FPS1
-                grid1 = None
-                if self.sa1._can_fuse(xyz, features):
-                    sorted_fps = self.fps_grid and fused.fps_grid_supported(xyz.size(1), self.sa1.npoint)
-                    grid1 = fused.prebuild_ball_query_grid(xyz, self.sa1.radius, inline=sorted_fps)
-                if grid1 is not None and grid1[1] is None:
-                    inds1, xyz1 = fused.furthest_point_sample_grid(xyz, self.sa1.npoint, grid1)
-                else:
-                    inds1, xyz1 = pointnet2_utils.furthest_point_sample_with_xyz(xyz, self.sa1.npoint)
-                done1 = None
+                inds1, xyz1 = pointnet2_utils.furthest_point_sample_with_xyz(xyz, self.sa1.npoint)
             levels = self._sample_lower_levels(xyz1)
             # grids of levels 2-4: each needs the coordinates one sampling level up
             grids = [fused.prebuild_ball_query_grid(xyz1, self.sa2.radius),
                      fused.prebuild_ball_query_grid(levels[0][1], self.sa3.radius, after=levels[0][2]),
                      fused.prebuild_ball_query_grid(levels[1][1], self.sa4.radius, after=levels[1][2])]
-            if piped is None:
-                xyz1, feats1, inds1 = self.sa1(xyz, features, inds1, new_xyz=xyz1, grid=grid1)
-            else:
-                main.wait_event(done1)
+            xyz1, feats1, inds1 = self.sa1(xyz, features, inds1, new_xyz=xyz1, grid=grid1)
             outs = [(xyz1, feats1, inds1)]
             xyz, features = xyz1, feats1
             for sa, (inds, new_xyz, event), grid in zip((self.sa2, self.sa3, self.sa4), levels, grids):

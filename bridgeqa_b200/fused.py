@@ -404,67 +404,6 @@ def side_stream(device, tag):
     return _side_streams[key]
 
 
-def sa_forward_pipelined(xyz, features, npoint, radius, nsample, normalize_xyz, packed, slices=4,
-                         exclusive=True):
-    """Sampling + grouping + MLP of one SA layer as a software pipeline: the furthest point
-    sampling is issued in `slices` resumable slices on the current stream, and the ball query +
-    fused MLP of the centres a slice produced run on a side stream underneath the following
-    slices (FPS is a serial latency chain that leaves a third of the SMs idle; its slices are
-    launched SM-exclusive so the consumers do not slow that chain down).  Results are identical
-    to sampling first and grouping afterwards.
-
-    Returns (inds, new_xyz, new_features, done_event); new_features is complete once
-    `done_event` (recorded on the side stream) has fired."""
-    N.check_tensor(xyz, "xyz", _f32)
-    b, n, _ = xyz.shape
-    dev = xyz.device
-    m = int(npoint)
-    inds = torch.empty((b, m), dtype=torch.int32, device=dev)
-    new_xyz = torch.empty((b, m, 3), dtype=_f32, device=dev)
-    state = torch.empty((b, n), dtype=_f32, device=dev)
-    idx = torch.empty((b, m, nsample), dtype=torch.int32, device=dev)
-    out_cm = torch.empty((b, packed.c3, m), dtype=_f32, device=dev)
-    out_pm = torch.empty((b, m, packed.c3), dtype=_f32, device=dev)
-    if features is not None:
-        pm = point_major(features)
-        c, stride = pm.size(2), pm.stride(1)
-    else:
-        pm, c, stride = None, 0, 0
-    main = torch.cuda.current_stream(dev)
-    side = side_stream(dev, "sa_consumer")
-    step = m // slices
-    bounds = [k * step for k in range(slices)] + [m]
-    ready = torch.cuda.Event()
-    ready.record(main)
-    side.wait_event(ready)                     # inputs (and the buffers above) exist
-    with torch.cuda.device(dev):
-        for k in range(slices):
-            lo, hi = bounds[k], bounds[k + 1]
-            N.call("bqa_furthest_point_sampling_slice", b, n, m, max(lo, 1), hi, N.ptr(xyz), N.ptr(inds),
-                   N.ptr(new_xyz), N.ptr(state), 1 if exclusive else 0, N.stream_ptr(dev))
-            sampled = torch.cuda.Event()
-            sampled.record(main)
-            with torch.cuda.stream(side):
-                side.wait_event(sampled)
-                nbytes = N.lib().bqa_ball_query_workspace_bytes(b, n, hi - lo, int(nsample))
-                work = torch.empty((nbytes,), dtype=torch.uint8, device=dev) if nbytes else None
-                N.call("bqa_ball_query_slice", b, n, m, lo, hi - lo, ctypes.c_float(radius), int(nsample),
-                       N.ptr(new_xyz), N.ptr(xyz), N.ptr(idx), N.ptr(work), N.stream_ptr(dev))
-                N.call("bqa_sa_mlp_max_forward_slice", b, n, m, lo, hi - lo, int(nsample), c, N.ptr(xyz),
-                       N.ptr(new_xyz), N.ptr(pm), stride, N.ptr(idx), ctypes.c_float(radius),
-                       1 if normalize_xyz else 0, packed.c1, packed.c2, packed.c3,
-                       N.ptr(packed.packed[0]), N.ptr(packed.bias[0]), N.ptr(packed.packed[1]),
-                       N.ptr(packed.bias[1]), N.ptr(packed.packed[2]), N.ptr(packed.bias[2]),
-                       N.ptr(out_cm), N.ptr(out_pm), packed.precision, N.stream_ptr(dev))
-        done = torch.cuda.Event()
-        with torch.cuda.stream(side):
-            done.record(side)
-    for t in (inds, new_xyz, state, idx, out_cm, out_pm, xyz) + ((pm,) if pm is not None else ()):
-        t.record_stream(side)
-    out_cm._bqa_pm = out_pm
-    return inds, new_xyz, out_cm, done
-
-
 def fp_forward(unknown, known, unknow_feats, known_feats, packed):
     """-> new_features (B, C2, n) fp32, with a point-major twin attached as ._bqa_pm."""
     N.check_tensor(unknown, "unknown", _f32)

@@ -149,18 +149,6 @@ class PointnetSAModuleVotes(nn.Module):
             self._fused_cache = (sig, fused.fold_sa_mlp(self.mlp_module))
         return self._fused_cache[1]
 
-    def forward_pipelined(self, xyz, features=None, slices=4, exclusive=True):
-        """Inference only: FPS in resumable slices with ball query + fused MLP of each slice's
-        centres running underneath the next slice (fused.sa_forward_pipelined).  Returns
-        (new_xyz, new_features, inds, done_event) or None when the layer cannot take this path."""
-        if not (self._can_fuse(xyz, features) and self.npoint % slices == 0
-                and (self.npoint // slices * self.nsample) % 128 == 0):
-            return None
-        inds, new_xyz, feats, done = fused.sa_forward_pipelined(
-            xyz, features, self.npoint, self.radius, self.nsample, self.normalize_xyz, self._packed(),
-            slices, exclusive)
-        return new_xyz, feats, inds, done
-
     def forward(self, xyz, features=None, inds=None, new_xyz=None, grid=None):
         """`new_xyz` (optional, beyond the reference signature): the centres xyz[inds] when the
         caller already has them (e.g. from the FPS kernel's epilogue), skipping the gather.

@@ -217,17 +217,6 @@ BQA_API int bqa_sa_mlp_max_forward(int b, int n, int npoint, int nsample, int c,
                                    const float *b2, const void *w3p, const float *b3,
                                    float *out_cm, float *out_pm, int precision, void *stream);
 
-/* Slice form: only the centres [j_begin, j_begin + j_count) of each scene's npoint_total centres
- * are processed; new_xyz, idx, out_cm and out_pm keep their full-size layouts (j_count * nsample
- * must be a multiple of 128). */
-BQA_API int bqa_sa_mlp_max_forward_slice(int b, int n, int npoint_total, int j_begin, int j_count,
-                                         int nsample, int c, const float *xyz, const float *new_xyz,
-                                         const float *feat_pm, int feat_stride, const int *idx,
-                                         float radius, int normalize_xyz, int c1, int c2, int c3,
-                                         const void *w1p, const float *b1, const void *w2p,
-                                         const float *b2, const void *w3p, const float *b3,
-                                         float *out_cm, float *out_pm, int precision, void *stream);
-
 /* ---- fused set-abstraction layer, warp-specialised form (csrc/sa_fused_v2.cu) ------------------
  * Same contract and arithmetic class as bqa_sa_mlp_max_forward (same reference lines:
  * pointnet2_utils.py:317-376 + pytorch_utils.py:11-36 + pointnet2_modules.py:259-262), different

@@ -310,28 +310,6 @@ def test_fp_module_backward_matches_torch_autograd():
     torch.testing.assert_close(g_kf, kf2.grad, rtol=1e-3, atol=1e-5)
 
 
-def test_pipelined_sa_equals_sequential_sa(_restore_fused):
-    """forward_pipelined (FPS slices with their ball query + fused MLP underneath on a side
-    stream) returns bit-identical indices, centres AND features to the sequential fused path:
-    it is the same arithmetic issued in a different order."""
-    sa = pm.PointnetSAModuleVotes(npoint=512, radius=0.3, nsample=32, mlp=[7, 64, 64, 128],
-                                  use_xyz=True, normalize_xyz=True)
-    sa = synthetic.fill_state_dict(sa, seed=12).cuda().eval()
-    pc = synthetic.make_batch(3, 20000, 7, first_scene=44).cuda()
-    xyz, feats = pc[..., :3].contiguous(), pc[..., 3:].transpose(1, 2).contiguous()
-    with torch.no_grad():
-        ref_xyz, ref_feats, ref_inds = sa(xyz, feats)
-        out = sa.forward_pipelined(xyz, feats, slices=4)
-        assert out is not None
-        new_xyz, new_feats, inds, done = out
-        torch.cuda.current_stream().wait_event(done)
-        torch.cuda.synchronize()
-    assert torch.equal(inds, ref_inds) and torch.equal(new_xyz, ref_xyz)
-    assert torch.equal(new_feats, ref_feats)
-    assert torch.equal(new_feats._bqa_pm, ref_feats._bqa_pm)
-
-
-@pytest.mark.parametrize("which,c", [("backbone", 7), ("detector", 132)])
 def test_cuda_graph_replay_equals_eager(which, c, _restore_fused):
     """graphs.GraphedForward: replaying the captured forward (three streams, ~35 launches) gives
     bit-identical results to issuing it eagerly, follows new inputs, new input buffers
