@@ -59,7 +59,8 @@ _SIGNATURES = {
     "bqa_three_interpolate_grad": ([_I, _I, _I, _I, _P, _P, _P, _P, _P], _I),
     "bqa_transpose_to_point_major": ([_I, _I, _I, _P, _P, _P], _I),
     "bqa_fp_mlp_supported": ([_I, _I, _I, _I, _I, _I], _I),
-    "bqa_fp_mlp_forward": ([_I, _I, _I, _I, _I, _P, _P, _P, _I, _P, _I, _I, _I, _P, _P, _P, _P, _P, _I, _P], _I),
+    "bqa_fp_mlp_forward": ([_I, _I, _I, _I, _I, _P, _P, _P, _I, _P, _I, _I, _I, _P, _P, _P, _P, _P, _I, _P,
+                            _P, _I], _I),
     "bqa_pack_weight_16": ([_I, _I, _I, _I, _I, _P, _P, _P], _I),
     "bqa_sa_mlp_max_supported": ([_I, _I, _I, _I, _I, _I], _I),
     "bqa_pack_weight_16_v2": ([_I, _I, _I, _I, _I, _P, _P, _P, _P], _I),

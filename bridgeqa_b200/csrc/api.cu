@@ -129,7 +129,7 @@ int fp_forward_dispatch(int b, int n, int m, int c_known, int c_skip, const floa
                         const float *known, const float *known_feat, int known_stride,
                         const float *skip_feat, int skip_stride, int c1, int c2, const void *w,
                         const float *b1, const float *b2, float *out_cm, float *out_pm, int fp16,
-                        cudaStream_t stream);
+                        cudaStream_t stream, const void *skip16, int skip16_stride);
 
 }  // namespace bqa
 
@@ -466,15 +466,17 @@ int bqa_fp_mlp_forward(int b, int n, int m, int c_known, int c_skip, const float
                        const float *known, const float *known_feat, int known_stride,
                        const float *skip_feat, int skip_stride, int c1, int c2, const void *w,
                        const float *b1, const float *b2, float *out_cm, float *out_pm, int precision,
-                       void *stream) {
+                       void *stream, const void *skip16, int skip16_stride) {
   NONNEG(b); NONNEG(n); NONNEG(m);
   if ((long long)b * n == 0) return BQA_OK;
   BQA_REQUIRE(precision == 0 || precision == 1, "%s: precision must be 0 (bf16) or 1 (fp16)", __func__);
-  PTR(unknown); PTR(known); PTR(known_feat); PTR(skip_feat); PTR(w); PTR(b1); PTR(b2); PTR(out_cm);
-  BQA_REQUIRE(known_stride >= c_known && skip_stride >= c_skip, "%s: row strides too small", __func__);
+  PTR(unknown); PTR(known); PTR(known_feat); PTR(w); PTR(b1); PTR(b2); PTR(out_cm);
+  BQA_REQUIRE(skip_feat != nullptr || skip16 != nullptr, "%s: skip_feat and skip16 are both NULL", __func__);
+  BQA_REQUIRE(known_stride >= c_known && (skip_feat == nullptr || skip_stride >= c_skip),
+              "%s: row strides too small", __func__);
   return fp_forward_dispatch(b, n, m, c_known, c_skip, unknown, known, known_feat, known_stride,
                              skip_feat, skip_stride, c1, c2, w, b1, b2, out_cm, out_pm, precision,
-                             (cudaStream_t)stream);
+                             (cudaStream_t)stream, skip16, skip16_stride);
 }
 
 int bqa_nn_distance(int b, int n, int m, const float *pc1, const float *pc2, int mode, float delta,

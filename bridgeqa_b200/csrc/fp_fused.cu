@@ -23,6 +23,8 @@
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
 
+#include <cstdio>
+
 #include "common.cuh"
 #include "tcgen05.cuh"
 
@@ -32,7 +34,7 @@ namespace {
 constexpr int kRows = 128;
 constexpr int kChunk = 64;         // K per weight slice
 constexpr int kWidth = 256;        // C1 == C2 == 256 (both FP layers of the backbone)
-constexpr int kKnownTile = 512;    // known points staged per pass of three_nn
+constexpr int kKnownTile = 512;    // known points staged per pass of three_nn (as float4: 8 KB)
 
 // two fp32 -> one packed 16-bit pair in one instruction (fp16 saturates at +-65504; see sa_fused.cu)
 __device__ __forceinline__ uint32_t pack16(float lo, float hi, int fp16) {
@@ -58,8 +60,10 @@ __device__ __forceinline__ void bulk_load(uint32_t dst, const void *src, uint32_
 struct FpParams {
   int b, n, m, c_known, c_skip;
   int known_stride, skip_stride;          // floats between consecutive points
+  int skip16_stride;                      // 16-bit elements between consecutive points of skip16
   const float *unknown, *known;           // (b,n,3), (b,m,3)
-  const float *known_feat, *skip_feat;    // point-major
+  const float *known_feat, *skip_feat;    // point-major f32
+  const uint16_t *skip16;                 // optional 16-bit point-major twin of the skip features (else NULL)
   const uint4 *w;                         // W1 image [(ck+cs)/8][256] then W2 image [256/8][256], 16-byte vectors
   const float *b1, *b2;
   float *out_cm, *out_pm;
@@ -67,7 +71,28 @@ struct FpParams {
   int num_tiles, tiles_per_scene;
 };
 
-__global__ void __launch_bounds__(kRows)
+#ifdef BQA_SA_TRACE
+__device__ long long g_fp_trace[64];
+#define FP_TRACE(i) if (blockIdx.x == 0 && threadIdx.x == 0) g_fp_trace[i] = clock64();
+#else
+#define FP_TRACE(i)
+#endif
+
+constexpr int kThreads = 256;      // 8 warps: two threads per row (warp w and w + 4 share TMEM lane quarter w % 4)
+
+struct NnRow { int i1, i2, i3; float w1, w2, w3; };
+
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void *src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+
+// lexicographic (distance, index) "less": the order the reference's strict-< cascade over ascending
+// indices produces (interpolate_gpu.cu:9-58)
+__device__ __forceinline__ bool nn_less(float da, int ia, float db, int ib) {
+  return da < db || (da == db && ia < ib);
+}
+
+__global__ void __launch_bounds__(kThreads)
 fp_mlp_kernel(const FpParams P) {
   constexpr int kAVecs = kChunk / 8 * kRows;          // 1024 x 16 B = 16 KB per stage
   constexpr int kWVecs = kChunk / 8 * kWidth;         // 2048 x 16 B = 32 KB per stage
@@ -76,15 +101,20 @@ fp_mlp_kernel(const FpParams P) {
   uint4 *a_st = reinterpret_cast<uint4 *>(smem_raw);                  // [2][kAVecs]
   uint4 *w_st = a_st + 2 * kAVecs;                                    // [2][kWVecs]
   uint4 *x1 = w_st + 2 * kWVecs;                                      // [kXVecs]
-  float *s_known = reinterpret_cast<float *>(x1 + kXVecs);            // [kKnownTile * 3]
-  float *s_b1 = s_known + kKnownTile * 3;
+  float *s_known = reinterpret_cast<float *>(x1 + kXVecs);            // [kKnownTile] float4 {x, y, z, -}
+  float *s_b1 = s_known + kKnownTile * 4;
   float *s_b2 = s_b1 + kWidth;
-  uint64_t *s_bar = reinterpret_cast<uint64_t *>(s_b2 + kWidth);      // wfull[2], mdone[2]
+  NnRow *s_nn = reinterpret_cast<NnRow *>(s_b2 + kWidth);             // [kRows]: neighbours + weights of every row
+  float *s_merge = reinterpret_cast<float *>(s_nn + kRows);           // [kRows][6]: second half's candidates
+  uint64_t *s_bar = reinterpret_cast<uint64_t *>(s_merge + kRows * 6);  // wfull[2], mdone[2]
   uint32_t *s_tmem = reinterpret_cast<uint32_t *>(s_bar + 4);
 
   const int tid = threadIdx.x;
-  const int warp = tid >> 5;
-  for (int i = tid; i < kWidth; i += kRows) { s_b1[i] = P.b1[i]; s_b2[i] = P.b2[i]; }
+  const int warp = tid >> 5, lane = tid & 31;
+  const int quarter = warp & 3;            // TMEM lane quarter of this warp
+  const int half = warp >> 2;              // 0 / 1: which half of the known set / of the columns this thread takes
+  const int row = quarter * 32 + lane;     // row of the tile this thread shares with thread (row, half ^ 1)
+  for (int i = tid; i < kWidth; i += kThreads) { s_b1[i] = P.b1[i]; s_b2[i] = P.b2[i]; }
   const uint32_t wfull0 = smem_u32(&s_bar[0]), mdone0 = smem_u32(&s_bar[2]);
   if (tid == 0) {
     for (int i = 0; i < 4; ++i) mbar_init(smem_u32(&s_bar[i]), 1);
@@ -98,6 +128,7 @@ fp_mlp_kernel(const FpParams P) {
   const uint32_t tmem_d1 = tmem, tmem_d2 = tmem + kWidth;
   const uint32_t a_addr = smem_u32(a_st), w_addr = smem_u32(w_st), x_addr = smem_u32(x1);
   const uint32_t idesc = umma::instr_desc_16b_f32(128, kWidth, !P.fp16);
+  const uint32_t lane_addr = (uint32_t)(quarter * 32) << 16;
 
   const int nk1 = (P.c_known + P.c_skip) / kChunk;   // weight slices of layer 1
   const int nk2 = kWidth / kChunk;                   // of layer 2
@@ -107,8 +138,8 @@ fp_mlp_kernel(const FpParams P) {
   for (int tile = blockIdx.x; tile < P.num_tiles; tile += gridDim.x) {
     const int scene = tile / P.tiles_per_scene;
     const int row0 = (tile % P.tiles_per_scene) * kRows;
-    const bool live = row0 + tid < P.n;
-    const int j = live ? row0 + tid : P.n - 1;       // clamp: dead rows compute, never store
+    const bool live = row0 + row < P.n;
+    const int j = live ? row0 + row : P.n - 1;       // clamp: dead rows compute, never store
 
     // first weight slice can fly while three_nn runs (both stages are idle between tiles)
     if (tid == 0) {
@@ -117,7 +148,25 @@ fp_mlp_kernel(const FpParams P) {
       bulk_load(w_addr + s * kWVecs * 16, P.w, kWVecs * 16, wfull0 + 8 * s);
     }
 
-    // ---- three_nn (interpolate_gpu.cu:9-58 semantics) + weights (pointnet2_modules.py:399-402)
+    // ---- the skip half of the layer-1 operand does not depend on the neighbours: when the previous fused
+    // layer left a 16-bit twin, ALL its chunks are copied now (cp.async, landing under three_nn and the
+    // interpolation) into the X1 buffer, which is idle until epilogue 1 -- which only runs after the last
+    // layer-1 MMA has read them
+    const bool skip_early = P.skip16 != nullptr && P.c_skip * kRows * 2 <= kXVecs * 16;
+    if (skip_early) {
+      const int g4e = lane >> 3;
+#pragma unroll 1
+      for (int it = 0; it < 2; ++it) {
+        const int r = warp * 16 + it * 8 + (lane & 7);
+        const int jr = min(row0 + r, P.n - 1);
+        const uint16_t *src = P.skip16 + ((size_t)scene * P.n + jr) * P.skip16_stride;
+        for (int q = g4e; q < P.c_skip / 8; q += 4) cp_async16(smem_u32(x1 + q * kRows + r), src + q * 8);
+      }
+    }
+    FP_TRACE(0)
+    // ---- three_nn (interpolate_gpu.cu:9-58 semantics) + weights (pointnet2_modules.py:399-402).
+    // The two threads of a row scan one half of every staged block of known points each; the reference's
+    // result is the three smallest (distance, index) pairs, so the halves merge exactly.
     float ux, uy, uz;
     {
       const float *u = P.unknown + ((size_t)scene * P.n + j) * 3;
@@ -126,37 +175,72 @@ fp_mlp_kernel(const FpParams P) {
     float best1 = INFINITY, best2 = INFINITY, best3 = INFINITY;
     int i1 = 0, i2 = 0, i3 = 0;
     const float *known = P.known + (size_t)scene * P.m * 3;
+    float4 *s_known4 = reinterpret_cast<float4 *>(s_known);
     for (int base = 0; base < P.m; base += kKnownTile) {
       const int tn = min(kKnownTile, P.m - base);
       __syncthreads();
-      for (int t = tid; t < tn * 3; t += kRows) s_known[t] = known[(size_t)base * 3 + t];
+      for (int t = tid; t < tn; t += kThreads) {
+        const float *kp = known + (size_t)(base + t) * 3;
+        s_known4[t] = make_float4(kp[0], kp[1], kp[2], 0.f);
+      }
       __syncthreads();
+      const int hn = (tn + 1) / 2;
+      const int t0 = half * hn, t1 = min(tn, t0 + hn);
+      // Ascending k inside this thread's range, so "strictly smaller than the current j-th best" is the
+      // reference's cascade; the insert is branch-free, and skipped for the whole warp when no lane's
+      // third-best improves (the common case after the first few dozen points).
 #pragma unroll 4
-      for (int t = 0; t < tn; ++t) {
-        const float d = sqdist3(ux, uy, uz, s_known[t * 3], s_known[t * 3 + 1], s_known[t * 3 + 2]);
-        const int k = base + t;
-        if (d < best1) {
-          best3 = best2; i3 = i2; best2 = best1; i2 = i1; best1 = d; i1 = k;
-        } else if (d < best2) {
-          best3 = best2; i3 = i2; best2 = d; i2 = k;
-        } else if (d < best3) {
-          best3 = d; i3 = k;
+      for (int t = t0; t < t1; ++t) {
+        const float4 kq = s_known4[t];
+        const float d = sqdist3(ux, uy, uz, kq.x, kq.y, kq.z);
+        if (__any_sync(0xffffffffu, d < best3)) {
+          const int k = base + t;
+          const bool l1 = d < best1, l2 = d < best2, l3 = d < best3;
+          best3 = l2 ? best2 : (l3 ? d : best3); i3 = l2 ? i2 : (l3 ? k : i3);
+          best2 = l1 ? best1 : (l2 ? d : best2); i2 = l1 ? i1 : (l2 ? k : i2);
+          best1 = l1 ? d : best1;                i1 = l1 ? k : i1;
         }
       }
     }
-    float w1, w2, w3;
-    {
-      const float r1 = __fdiv_rn(1.0f, __fadd_rn(__fsqrt_rn(best1), 1e-8f));
-      const float r2 = __fdiv_rn(1.0f, __fadd_rn(__fsqrt_rn(best2), 1e-8f));
-      const float r3 = __fdiv_rn(1.0f, __fadd_rn(__fsqrt_rn(best3), 1e-8f));
-      const float norm = __fadd_rn(__fadd_rn(r1, r2), r3);
-      w1 = __fdiv_rn(r1, norm); w2 = __fdiv_rn(r2, norm); w3 = __fdiv_rn(r3, norm);
+    if (half == 1) {
+      float *mg = s_merge + row * 6;
+      mg[0] = best1; mg[1] = best2; mg[2] = best3;
+      mg[3] = __int_as_float(i1); mg[4] = __int_as_float(i2); mg[5] = __int_as_float(i3);
     }
-    const float *f1 = P.known_feat + ((size_t)scene * P.m + i1) * P.known_stride;
-    const float *f2 = P.known_feat + ((size_t)scene * P.m + i2) * P.known_stride;
-    const float *f3 = P.known_feat + ((size_t)scene * P.m + i3) * P.known_stride;
-    const float *fs = P.skip_feat + ((size_t)scene * P.n + j) * P.skip_stride;
+    __syncthreads();
+    if (half == 0) {
+      const float *mg = s_merge + row * 6;
+      float ad[3] = {best1, best2, best3}, bd[3] = {mg[0], mg[1], mg[2]};
+      int ai[3] = {i1, i2, i3}, bi[3] = {__float_as_int(mg[3]), __float_as_int(mg[4]), __float_as_int(mg[5])};
+      float od[3]; int oi[3];
+      int pa = 0, pb = 0;
+#pragma unroll
+      for (int t = 0; t < 3; ++t) {
+        // entries never filled keep (inf, 0) on both sides: either choice writes (inf, 0) like the reference
+        const float da = pa == 0 ? ad[0] : pa == 1 ? ad[1] : ad[2];
+        const float db = pb == 0 ? bd[0] : pb == 1 ? bd[1] : bd[2];
+        const int ia = pa == 0 ? ai[0] : pa == 1 ? ai[1] : ai[2];
+        const int ib = pb == 0 ? bi[0] : pb == 1 ? bi[1] : bi[2];
+        const bool take_b = nn_less(db, ib, da, ia);
+        od[t] = take_b ? db : da; oi[t] = take_b ? ib : ia;
+        if (take_b) ++pb; else ++pa;
+      }
+      const float r1 = __fdiv_rn(1.0f, __fadd_rn(__fsqrt_rn(od[0]), 1e-8f));
+      const float r2 = __fdiv_rn(1.0f, __fadd_rn(__fsqrt_rn(od[1]), 1e-8f));
+      const float r3 = __fdiv_rn(1.0f, __fadd_rn(__fsqrt_rn(od[2]), 1e-8f));
+      const float norm = __fadd_rn(__fadd_rn(r1, r2), r3);
+      NnRow nr;
+      nr.i1 = oi[0]; nr.i2 = oi[1]; nr.i3 = oi[2];
+      nr.w1 = __fdiv_rn(r1, norm); nr.w2 = __fdiv_rn(r2, norm); nr.w3 = __fdiv_rn(r3, norm);
+      s_nn[row] = nr;
+    }
+    __syncthreads();
 
+    FP_TRACE(1)
+    // ---- gather geometry: a warp serves 16 rows of the tile, 8 at a time; lane = (row r8, chunk group g):
+    // the four lanes of a row read 4 x 32 contiguous bytes of each source row (full 128-byte lines) and
+    // a quarter warp writes 8 consecutive rows of one 16-byte chunk column (conflict-free)
+    const int g4 = lane >> 3;
     for (int c = 0; c < nchunks; ++c) {
       const uint32_t g = gchunk + c, s = g & 1;
       // stage s^1 is free once the MMAs of slice g-1 are done: prefetch the next weights
@@ -169,46 +253,83 @@ fp_mlp_kernel(const FpParams P) {
         }
       }
       if (c < nk1) {
-        // ---- this thread's row of the layer-1 A operand, channels [c*64, c*64+64) ----------
+        // ---- layer-1 A operand, channels [c*64, c*64+64) of all 128 rows ---------------------
         uint4 *dst = a_st + s * kAVecs;
         const int k0 = c * kChunk;
-        if (k0 < P.c_known) {
-#pragma unroll 2
-          for (int q = 0; q < kChunk / 8; ++q) {
-            float v[8];
 #pragma unroll
-            for (int h = 0; h < 2; ++h) {
-              const float4 p1 = __ldg(reinterpret_cast<const float4 *>(f1 + k0 + q * 8 + h * 4));
-              const float4 p2 = __ldg(reinterpret_cast<const float4 *>(f2 + k0 + q * 8 + h * 4));
-              const float4 p3 = __ldg(reinterpret_cast<const float4 *>(f3 + k0 + q * 8 + h * 4));
-              v[h * 4 + 0] = __fmaf_rn(p3.x, w3, __fmaf_rn(p1.x, w1, __fmul_rn(p2.x, w2)));
-              v[h * 4 + 1] = __fmaf_rn(p3.y, w3, __fmaf_rn(p1.y, w1, __fmul_rn(p2.y, w2)));
-              v[h * 4 + 2] = __fmaf_rn(p3.z, w3, __fmaf_rn(p1.z, w1, __fmul_rn(p2.z, w2)));
-              v[h * 4 + 3] = __fmaf_rn(p3.w, w3, __fmaf_rn(p1.w, w1, __fmul_rn(p2.w, w2)));
+        for (int it = 0; it < 2; ++it) {
+          const int r = warp * 16 + it * 8 + (lane & 7);
+          const int jr = min(row0 + r, P.n - 1);
+          if (k0 < P.c_known) {
+            const NnRow nr = s_nn[r];
+            const float *f1 = P.known_feat + ((size_t)scene * P.m + nr.i1) * P.known_stride + k0;
+            const float *f2 = P.known_feat + ((size_t)scene * P.m + nr.i2) * P.known_stride + k0;
+            const float *f3 = P.known_feat + ((size_t)scene * P.m + nr.i3) * P.known_stride + k0;
+            // 12 independent 16-byte loads in flight before the first use (the rows are random: the
+            // loop is bound by their latency, not by arithmetic)
+            float4 p1[2][2], p2[2][2], p3[2][2];
+#pragma unroll
+            for (int qq = 0; qq < 2; ++qq) {
+#pragma unroll
+              for (int h = 0; h < 2; ++h) {
+                const int off = (g4 + 4 * qq) * 8 + h * 4;
+                p1[qq][h] = __ldg(reinterpret_cast<const float4 *>(f1 + off));
+                p2[qq][h] = __ldg(reinterpret_cast<const float4 *>(f2 + off));
+                p3[qq][h] = __ldg(reinterpret_cast<const float4 *>(f3 + off));
+              }
             }
-            dst[q * kRows + tid] = make_uint4(pack16(v[0], v[1], P.fp16), pack16(v[2], v[3], P.fp16),
+#pragma unroll
+            for (int qq = 0; qq < 2; ++qq) {
+              const int q = g4 + 4 * qq;
+              float v[8];
+#pragma unroll
+              for (int h = 0; h < 2; ++h) {
+                v[h * 4 + 0] = __fmaf_rn(p3[qq][h].x, nr.w3, __fmaf_rn(p1[qq][h].x, nr.w1, __fmul_rn(p2[qq][h].x, nr.w2)));
+                v[h * 4 + 1] = __fmaf_rn(p3[qq][h].y, nr.w3, __fmaf_rn(p1[qq][h].y, nr.w1, __fmul_rn(p2[qq][h].y, nr.w2)));
+                v[h * 4 + 2] = __fmaf_rn(p3[qq][h].z, nr.w3, __fmaf_rn(p1[qq][h].z, nr.w1, __fmul_rn(p2[qq][h].z, nr.w2)));
+                v[h * 4 + 3] = __fmaf_rn(p3[qq][h].w, nr.w3, __fmaf_rn(p1[qq][h].w, nr.w1, __fmul_rn(p2[qq][h].w, nr.w2)));
+              }
+              dst[q * kRows + r] = make_uint4(pack16(v[0], v[1], P.fp16), pack16(v[2], v[3], P.fp16),
                                               pack16(v[4], v[5], P.fp16), pack16(v[6], v[7], P.fp16));
-          }
-        } else {
-          const float *src = fs + (k0 - P.c_known);
-#pragma unroll 4
-          for (int q = 0; q < kChunk / 8; ++q) {
-            const float4 a = __ldg(reinterpret_cast<const float4 *>(src + q * 8));
-            const float4 bq = __ldg(reinterpret_cast<const float4 *>(src + q * 8 + 4));
-            dst[q * kRows + tid] = make_uint4(pack16(a.x, a.y, P.fp16), pack16(a.z, a.w, P.fp16),
+            }
+          } else if (skip_early) {
+            // already in the X1 buffer
+          } else if (P.skip16) {
+            // the previous fused layer's 16-bit twin: the very bits this operand needs
+            const uint16_t *src = P.skip16 + ((size_t)scene * P.n + jr) * P.skip16_stride + (k0 - P.c_known);
+#pragma unroll
+            for (int qq = 0; qq < 2; ++qq) {
+              const int q = g4 + 4 * qq;
+              cp_async16(smem_u32(dst + q * kRows + r), src + q * 8);
+            }
+          } else {
+            const float *src = P.skip_feat + ((size_t)scene * P.n + jr) * P.skip_stride + (k0 - P.c_known);
+#pragma unroll
+            for (int qq = 0; qq < 2; ++qq) {
+              const int q = g4 + 4 * qq;
+              const float4 a = __ldg(reinterpret_cast<const float4 *>(src + q * 8));
+              const float4 bq = __ldg(reinterpret_cast<const float4 *>(src + q * 8 + 4));
+              dst[q * kRows + r] = make_uint4(pack16(a.x, a.y, P.fp16), pack16(a.z, a.w, P.fp16),
                                               pack16(bq.x, bq.y, P.fp16), pack16(bq.z, bq.w, P.fp16));
+            }
           }
         }
+        asm volatile("cp.async.wait_all;" ::: "memory");
       }
+      FP_TRACE(2 + 3 * c)
       umma::fence_proxy_async_smem();
       umma::fence_before_sync();
       __syncthreads();
+      FP_TRACE(3 + 3 * c)
       if (tid == 0) {
         mbar_wait(wfull0 + 8 * s, (g >> 1) & 1);
         umma::fence_after_sync();
         const bool layer1 = c < nk1;
-        const uint32_t abase = layer1 ? a_addr + s * kAVecs * 16
-                                      : x_addr + (uint32_t)(c - nk1) * (kChunk / 8) * kRows * 16;
+        const int k0c = c * kChunk;
+        const bool early = layer1 && skip_early && k0c >= P.c_known;
+        const uint32_t abase = early ? x_addr + (uint32_t)((k0c - P.c_known) / 8) * kRows * 16
+                               : layer1 ? a_addr + s * kAVecs * 16
+                                        : x_addr + (uint32_t)(c - nk1) * (kChunk / 8) * kRows * 16;
 #pragma unroll
         for (int ks = 0; ks < kChunk / 16; ++ks) {
           const uint64_t ad = umma::smem_desc(abase + (uint32_t)(2 * ks) * kRows * 16, kRows * 16, 128);
@@ -219,14 +340,16 @@ fp_mlp_kernel(const FpParams P) {
         }
         umma::commit(mdone0 + 8 * s);
       }
+      FP_TRACE(4 + 3 * c)
       if (c == nk1 - 1) {
-        // ---- epilogue 1: X1 = relu(D1 + b1) as the 16-bit A operand of layer 2 ------------
+        // ---- epilogue 1: X1 = relu(D1 + b1) as the 16-bit A operand of layer 2; the two threads of a
+        // row convert 128 columns each
         mbar_wait(mdone0 + 8 * s, (g >> 1) & 1);
         umma::fence_after_sync();
-#pragma unroll 2
-        for (int c0 = 0; c0 < kWidth; c0 += 32) {
+#pragma unroll 1
+        for (int c0 = half * (kWidth / 2); c0 < (half + 1) * (kWidth / 2); c0 += 32) {
           uint32_t v[32];
-          umma::ld_32x32b_x32(tmem_d1 + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0, v);
+          umma::ld_32x32b_x32(tmem_d1 + lane_addr + (uint32_t)c0, v);
           umma::wait_ld();
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
@@ -238,24 +361,25 @@ fp_mlp_kernel(const FpParams P) {
               const float hi = __uint_as_float(v[q * 8 + e * 2 + 1]) + s_b1[col + 1];
               p[e] = pack16_relu(lo, hi, P.fp16);
             }
-            x1[(c0 / 8 + q) * kRows + tid] = make_uint4(p[0], p[1], p[2], p[3]);
+            x1[(c0 / 8 + q) * kRows + row] = make_uint4(p[0], p[1], p[2], p[3]);
           }
         }
       }
     }
     gchunk += nchunks;
+    FP_TRACE(40)
 
-    // ---- epilogue 2: out = relu(D2 + b2), channel-major and point-major -------------------
+    // ---- epilogue 2: out = relu(D2 + b2), channel-major and (optionally) point-major ----------
     {
       const uint32_t g = gchunk - 1, s = g & 1;
       mbar_wait(mdone0 + 8 * s, (g >> 1) & 1);
       umma::fence_after_sync();
       float *opm = P.out_pm ? P.out_pm + ((size_t)scene * P.n + j) * kWidth : nullptr;
       float *ocm = P.out_cm + (size_t)scene * kWidth * P.n + j;
-#pragma unroll 2
-      for (int c0 = 0; c0 < kWidth; c0 += 32) {
+#pragma unroll 1
+      for (int c0 = half * (kWidth / 2); c0 < (half + 1) * (kWidth / 2); c0 += 32) {
         uint32_t v[32];
-        umma::ld_32x32b_x32(tmem_d2 + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0, v);
+        umma::ld_32x32b_x32(tmem_d2 + lane_addr + (uint32_t)c0, v);
         umma::wait_ld();
         float o[32];
 #pragma unroll
@@ -271,9 +395,11 @@ fp_mlp_kernel(const FpParams P) {
         }
       }
     }
+    FP_TRACE(41)
     umma::fence_before_sync();
     __syncthreads();       // TMEM, X1 and both stages are free for the next tile
     umma::fence_after_sync();
+    FP_TRACE(42)
   }
   __syncthreads();
   if (warp == 0) umma::tmem_dealloc(tmem, 512);
@@ -292,28 +418,44 @@ int fp_forward_dispatch(int b, int n, int m, int c_known, int c_skip, const floa
                         const float *known, const float *known_feat, int known_stride,
                         const float *skip_feat, int skip_stride, int c1, int c2, const void *w,
                         const float *b1, const float *b2, float *out_cm, float *out_pm, int fp16,
-                        cudaStream_t stream) {
+                        cudaStream_t stream, const void *skip16, int skip16_stride) {
   if (!fp_supported(n, m, c_known, c_skip, c1, c2))
     return set_error(BQA_ERR_UNSUPPORTED, "fp_mlp: unsupported shape c_known=%d c_skip=%d mlp=%d,%d",
                      c_known, c_skip, c1, c2);
-  if ((known_stride % 4) || (skip_stride % 4) || (reinterpret_cast<uintptr_t>(known_feat) & 15) ||
-      (reinterpret_cast<uintptr_t>(skip_feat) & 15) || (reinterpret_cast<uintptr_t>(out_pm) & 15))
+  if ((known_stride % 4) || (reinterpret_cast<uintptr_t>(known_feat) & 15) ||
+      (skip_feat && ((skip_stride % 4) || (reinterpret_cast<uintptr_t>(skip_feat) & 15))) ||
+      (reinterpret_cast<uintptr_t>(out_pm) & 15))
     return set_error(BQA_ERR_INVALID_ARG, "fp_mlp: point-major features must be 16-byte aligned rows");
   FpParams P;
   P.b = b; P.n = n; P.m = m; P.c_known = c_known; P.c_skip = c_skip;
   P.known_stride = known_stride; P.skip_stride = skip_stride;
   P.unknown = unknown; P.known = known; P.known_feat = known_feat; P.skip_feat = skip_feat;
+  P.skip16 = (const uint16_t *)skip16; P.skip16_stride = skip16_stride;
+  if (skip16 && ((skip16_stride % 8) || skip16_stride < c_skip || (reinterpret_cast<uintptr_t>(skip16) & 15)))
+    return set_error(BQA_ERR_INVALID_ARG, "fp_mlp: skip16 rows must be 16-byte aligned and hold c_skip values");
   P.w = (const uint4 *)w; P.b1 = b1; P.b2 = b2; P.out_cm = out_cm; P.out_pm = out_pm; P.fp16 = fp16;
   P.tiles_per_scene = ceil_div(n, kRows);
   P.num_tiles = b * P.tiles_per_scene;
   const size_t smem = 16 * (2 * (size_t)(kChunk / 8 * kRows) + 2 * (size_t)(kChunk / 8 * kWidth) +
-                            (size_t)(kWidth / 8 * kRows)) + 4 * (kKnownTile * 3 + 2 * kWidth) + 32 + 16;
+                            (size_t)(kWidth / 8 * kRows)) + 4 * (kKnownTile * 4 + 2 * kWidth) +
+                      sizeof(NnRow) * kRows + 4 * 6 * kRows + 32 + 16;
   BQA_CUDA(cudaFuncSetAttribute(fp_mlp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int dev = 0, sms = 148;
   BQA_CUDA(cudaGetDevice(&dev));
   BQA_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   const int grid = min(P.num_tiles, sms);
-  fp_mlp_kernel<<<grid, kRows, smem, stream>>>(P);
+  fp_mlp_kernel<<<grid, kThreads, smem, stream>>>(P);
+#ifdef BQA_SA_TRACE
+  {
+    long long t[64];
+    cudaMemcpyFromSymbol(t, g_fp_trace, sizeof(t));
+    fprintf(stderr, "[bqa fp trace] n=%d m=%d grid=%d | nn %lld |", n, m, grid, t[1] - t[0]);
+    for (int c = 0; c < 12; ++c)
+      fprintf(stderr, " c%d: build %lld sync %lld issue %lld |", c, t[2 + 3 * c] - (c ? t[4 + 3 * (c - 1)] : t[1]),
+              t[3 + 3 * c] - t[2 + 3 * c], t[4 + 3 * c] - t[3 + 3 * c]);
+    fprintf(stderr, " epi2 %lld | tail %lld | total %lld\n", t[41] - t[40], t[42] - t[41], t[42] - t[0]);
+  }
+#endif
   count_launch();
   return check_launch("fp_mlp_kernel");
 }

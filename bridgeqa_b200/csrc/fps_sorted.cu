@@ -40,6 +40,9 @@
 namespace bqa {
 
 const float4 *ball_query_grid_sorted(const void *grid, int b, int n);   // ball_query_grid.cu
+bool fps_stream_supported(int n, int m);                                 // fps_stream.cu
+int fps_stream_dispatch(int b, int n, int m, const float *xyz, const void *grid, int *idxs,
+                        float *new_xyz, cudaStream_t stream);
 
 namespace {
 
@@ -313,6 +316,11 @@ int fps_sorted_dispatch(int b, int n, int m, const float *xyz, const void *grid,
     return set_error(BQA_ERR_UNSUPPORTED, "fps (sorted): n=%d not supported", n);
   static const int env_lean = [] { const char *e = getenv("BQA_FPS_LEAN"); return e ? atoi(e) : -1; }();
   if (env_lean >= 0) lean = env_lean;                    // developer override
+  // throughput variant of choice: the one-SM kernel (fps_stream.cu).  BQA_FPS_STREAM=0 keeps the
+  // cluster kernels below, =2 also routes the latency variant through it (measurement only).
+  static const int env_stream = [] { const char *e = getenv("BQA_FPS_STREAM"); return e ? atoi(e) : 1; }();
+  if (((lean && env_stream) || env_stream == 2) && fps_stream_supported(n, m))
+    return fps_stream_dispatch(b, n, m, xyz, grid, idxs, new_xyz, stream);
   if (lean && fps_lean_supported(n, m)) {
     // fewest CTAs whose shared memory holds the scene; the tail of the last run is padding
     const int cs = ceil_div(n, kLeanT * kLeanMaxP);

@@ -55,6 +55,7 @@ class Pointnet2Backbone(nn.Module):
         self.fps_grid = os.environ.get("BQA_FPS_GRID", "1") != "0"
         self.fp1 = PointnetFPModule(mlp=[c + c, c, c])
         self.fp2 = PointnetFPModule(mlp=[c + c, c, seed_feat_dim])
+        self.fp2.emit_point_major = False      # nothing downstream gathers from fp2's output rows
 
     @staticmethod
     def _break_up_pc(pc):

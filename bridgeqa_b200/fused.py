@@ -404,20 +404,31 @@ def side_stream(device, tag):
     return _side_streams[key]
 
 
-def fp_forward(unknown, known, unknow_feats, known_feats, packed):
-    """-> new_features (B, C2, n) fp32, with a point-major twin attached as ._bqa_pm."""
+def fp_forward(unknown, known, unknow_feats, known_feats, packed, pm32=True):
+    """-> new_features (B, C2, n) fp32, with a point-major fp32 twin attached as ._bqa_pm when pm32 (the
+    next FP layer interpolates from it).  The skip features are taken from their 16-bit twin when the
+    layer that produced them attached one (bits identical to converting the fp32 values here)."""
     N.check_tensor(unknown, "unknown", _f32)
     N.check_tensor(known, "known", _f32)
     b, n, _ = unknown.shape
     m = known.size(1)
     kpm = point_major(known_feats)
-    spm = point_major(unknow_feats)
+    s16 = getattr(unknow_feats, "_bqa_pm16", None)
+    if not (s16 is not None and getattr(unknow_feats, "_bqa_pm16_prec", None) == packed.precision
+            and s16.device == unknown.device and s16.is_contiguous() and s16.dim() == 3
+            and s16.size(0) == b and s16.size(1) == n and s16.size(2) >= unknow_feats.size(1)
+            and s16.size(2) % 8 == 0):
+        s16 = None
+    spm = point_major(unknow_feats) if s16 is None else None
+    c_skip = unknow_feats.size(1)
     out_cm = torch.empty((b, packed.c2, n), dtype=_f32, device=unknown.device)
-    out_pm = torch.empty((b, n, packed.c2), dtype=_f32, device=unknown.device)
+    out_pm = torch.empty((b, n, packed.c2), dtype=_f32, device=unknown.device) if pm32 else None
     with torch.cuda.device(unknown.device):
-        N.call("bqa_fp_mlp_forward", b, n, m, kpm.size(2), spm.size(2), N.ptr(unknown), N.ptr(known),
-               N.ptr(kpm), kpm.stride(1), N.ptr(spm), spm.stride(1), packed.c1, packed.c2,
+        N.call("bqa_fp_mlp_forward", b, n, m, kpm.size(2), c_skip, N.ptr(unknown), N.ptr(known),
+               N.ptr(kpm), kpm.stride(1), N.ptr(spm), spm.stride(1) if spm is not None else 0, packed.c1, packed.c2,
                N.ptr(packed.image), N.ptr(packed.bias[0]), N.ptr(packed.bias[1]), N.ptr(out_cm),
-               N.ptr(out_pm), packed.precision, N.stream_ptr(unknown.device))
-    out_cm._bqa_pm = out_pm
+               N.ptr(out_pm), packed.precision, N.stream_ptr(unknown.device),
+               N.ptr(s16), s16.size(2) if s16 is not None else 0)
+    if out_pm is not None:
+        out_cm._bqa_pm = out_pm
     return out_cm

@@ -228,6 +228,9 @@ class PointnetFPModule(nn.Module):
         super().__init__()
         self.mlp = pt_utils.SharedMLP(mlp, bn=bn)
         self._fused_cache = None
+        # fused inference path: also emit the point-major fp32 copy of the output that a following
+        # fused FP layer interpolates from (the last FP layer of a backbone can switch it off)
+        self.emit_point_major = True
 
     def train(self, mode=True):
         self._fused_cache = None
@@ -241,7 +244,8 @@ class PointnetFPModule(nn.Module):
             sig = fused.weights_signature(self.mlp)
             if self._fused_cache is None or self._fused_cache[0] != sig:
                 self._fused_cache = (sig, fused.fold_fp_mlp(self.mlp))
-            return fused.fp_forward(unknown, known, unknow_feats, known_feats, self._fused_cache[1])
+            return fused.fp_forward(unknown, known, unknow_feats, known_feats, self._fused_cache[1],
+                                    pm32=self.emit_point_major)
 
         if known is not None:
             dist, idx = pointnet2_utils.three_nn(unknown, known)

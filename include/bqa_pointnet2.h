@@ -265,13 +265,17 @@ BQA_API int bqa_sa_mlp_max_forward_v2(int b, int n, int npoint, int nsample, int
  * pointnet2_modules.py:413.  w: layer-1 image (k_pad = c_known+c_skip) immediately followed
  * by the layer-2 image (k_pad = c1), both from bqa_pack_weight_16(xyz_first=0) with the same
  * `precision`; b1, b2 f32.  out_cm (b,c2,n) f32; out_pm (b,n,c2) f32 optional.
+ * skip16 (optional, else NULL): a 16-bit point-major copy of the skip features in `precision`'s
+ * format (what bqa_sa_mlp_max_forward_v2 writes as out_pm16), rows skip16_stride elements apart
+ * (multiple of 8): copied straight into the operand with cp.async; skip_feat may then be NULL.
  * bqa_fp_mlp_supported: c1 == c2 == 256 and c_known, c_skip multiples of 64. */
 BQA_API int bqa_fp_mlp_supported(int n, int m, int c_known, int c_skip, int c1, int c2);
 BQA_API int bqa_fp_mlp_forward(int b, int n, int m, int c_known, int c_skip, const float *unknown,
                                const float *known, const float *known_feat, int known_stride,
                                const float *skip_feat, int skip_stride, int c1, int c2,
                                const void *w, const float *b1, const float *b2, float *out_cm,
-                               float *out_pm, int precision, void *stream);
+                               float *out_pm, int precision, void *stream, const void *skip16,
+                               int skip16_stride);
 
 /* ---- nn_distance (first consumer of the hot path's outputs) -------------
  * replaces: utils/nn_distance.py:25-52 `nn_distance(pc1 (B,N,3), pc2 (B,M,3), l1smooth, delta, l1)`

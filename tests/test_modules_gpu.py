@@ -310,6 +310,7 @@ def test_fp_module_backward_matches_torch_autograd():
     torch.testing.assert_close(g_kf, kf2.grad, rtol=1e-3, atol=1e-5)
 
 
+@pytest.mark.parametrize("which,c", [("backbone", 7), ("detector", 132)])
 def test_cuda_graph_replay_equals_eager(which, c, _restore_fused):
     """graphs.GraphedForward: replaying the captured forward (three streams, ~35 launches) gives
     bit-identical results to issuing it eagerly, follows new inputs, new input buffers
