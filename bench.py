@@ -260,6 +260,8 @@ def sms_occupied(name, dims, sms=148):
     SM-time budget of the in-flight regime, where the step is bound by total SM-time, not by latency."""
     if name == "bqa_furthest_point_sampling_grid_lean":
         b, n = dims[:2]
+        if 512 <= n <= 57000:          # one-SM kernel (fps_stream.cu): one CTA per scene
+            return min(sms, b)
         return min(sms, b * -(-n // (768 * 18)))
     if name == "bqa_furthest_point_sampling_grid":
         b, n = dims[:2]
@@ -393,7 +395,7 @@ def main():
                     "forward instead of under the previous step's backward")
     ap.add_argument("--torch-bn", action="store_true", help="--mode train: torch BatchNorm/ReLU/max_pool modules "
                     "instead of the sm_100a streaming kernels (the reference's module structure)")
-    ap.add_argument("--in-flight", type=int, default=4,
+    ap.add_argument("--in-flight", type=int, default=8,
                     help="batches in flight (graphs.InFlight): consecutive steps are issued on a ring of this many "
                          "streams so the next batch's sampling chain runs under this batch's SA/FP kernels; 1 = serial")
     ap.add_argument("--bind-cpu", action="store_true",
@@ -469,6 +471,8 @@ def main():
     # inputs: 16 scenes per rank, resident in HBM in ROT rotated variants so that a step's
     # input was last touched ROT-1 steps (and >> 126 MB of other traffic) ago
     ROT = 8 if args.workload == "backbone" else 4     # a 132-d batch is 346 MB: larger than L2 on its own
+    if args.in_flight > ROT and args.workload == "backbone":
+        ROT = args.in_flight                          # one resident input (and graph) per forward in flight
     host_batch = synthetic.make_batch(BATCH, NUM_POINTS, features, first_scene=rank * BATCH)
     host_pinned = [torch.roll(host_batch, shifts=997 * i, dims=1).contiguous().pin_memory() for i in range(ROT)]
     dev_inputs = [h.to(device) for h in host_pinned]

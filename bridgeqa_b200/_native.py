@@ -16,6 +16,7 @@ SO_PATH = os.path.join(HERE, "lib", "libbqa_pointnet2.so")
 
 _I = ctypes.c_int
 _F = ctypes.c_float
+_D = ctypes.c_double
 _P = ctypes.c_void_p
 _LL = ctypes.c_longlong
 
@@ -35,6 +36,10 @@ _SIGNATURES = {
     "bqa_nn_distance": ([_I, _I, _I, _P, _P, _I, _F, _P, _P, _P, _P, _P], _I),
     "bqa_bn_relu_max_supported": ([_I], _I),
     "bqa_bn_train_stats": ([_I, _I, _LL, _P, _P, _F, _F, _P, _P, _P, _P, _P], _I),
+    "bqa_bn_finalize_shifted": ([_I, _D, _P, _P, _F, _F, _P, _P, _P, _P, _P], _I),
+    "bqa_conv1x1_tf32_supported": ([_I, _I, _I, _LL, _I], _I),
+    "bqa_conv1x1_tf32_forward": ([_I, _I, _I, _LL, _P, _P, _I, _P, _P, _P, _P], _I),
+    "bqa_conv1x1_tf32_wgrad": ([_I, _I, _I, _LL, _P, _P, _P, _P], _I),
     "bqa_bn_relu_forward": ([_I, _I, _LL, _P, _P, _P, _P, _P, _P, _P], _I),
     "bqa_bn_relu_max_forward": ([_I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P], _I),
     "bqa_bn_relu_backward": ([_I, _I, _LL, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P], _I),

@@ -50,6 +50,14 @@ int nms3d_dispatch(int b, int k, const float *boxes, const int *valid, double th
 int count_in_boxes_dispatch(int b, int n, int k, const float *xyz, const float *lohi, int *counts,
                             cudaStream_t stream);
 bool bn_relu_max_supported(int ns);
+int bn_finalize_shifted_dispatch(int c, double count, const double *sums, const float *shift, float eps,
+                                 float momentum, float *mean, float *invstd, float *running_mean,
+                                 float *running_var, cudaStream_t stream);
+bool conv1x1_tf32_supported(int b, int cin, int cout, long long p, int ldw);
+int conv1x1_tf32_forward(int b, int cin, int cout, int p, const float *x, const float *w, int ldw, float *y,
+                         const float *shift, double *sums, cudaStream_t stream);
+int conv1x1_tf32_wgrad(int b, int cin, int cout, int p, const float *x, const float *dy, float *dw,
+                       cudaStream_t stream);
 int bn_stats_dispatch(int b, int c, long long l, const float *y, double *sums, float eps, float momentum,
                       float *mean, float *invstd, float *running_mean, float *running_var,
                       cudaStream_t stream);
@@ -522,6 +530,45 @@ int bqa_bn_train_stats(int b, int c, long long l, const float *y, double *sums_s
   ALIGNED16(y);
   return bn_stats_dispatch(b, c, l, y, sums_scratch, eps, momentum, mean, invstd, running_mean, running_var,
                            (cudaStream_t)stream);
+}
+
+int bqa_bn_finalize_shifted(int c, double count, const double *sums, const float *shift, float eps,
+                            float momentum, float *mean, float *invstd, float *running_mean,
+                            float *running_var, void *stream) {
+  NONNEG(c);
+  if (c == 0) return BQA_OK;
+  BQA_REQUIRE(count > 0.0, "%s: batch statistics of an empty tensor", __func__);
+  PTR(sums); PTR(mean); PTR(invstd);
+  return bn_finalize_shifted_dispatch(c, count, sums, shift, eps, momentum, mean, invstd, running_mean,
+                                      running_var, (cudaStream_t)stream);
+}
+
+int bqa_conv1x1_tf32_supported(int b, int cin, int cout, long long p, int ldw) {
+  return conv1x1_tf32_supported(b, cin, cout, p, ldw) ? 1 : 0;
+}
+
+int bqa_conv1x1_tf32_forward(int b, int cin, int cout, long long p, const float *x, const float *w, int ldw,
+                             float *y, const float *shift, double *sums, void *stream) {
+  NONNEG(b); NONNEG(cin); NONNEG(cout);
+  BQA_REQUIRE(p >= 0, "%s: p must be >= 0", __func__);
+  if ((long long)b * cout * p == 0) return BQA_OK;
+  PTR(x); PTR(w); PTR(y);
+  BQA_REQUIRE(conv1x1_tf32_supported(b, cin, cout, p, ldw),
+              "%s: needs p %% 4 == 0, ldw %% 4 == 0, ldw >= cin (b=%d cin=%d cout=%d p=%lld ldw=%d)", __func__, b,
+              cin, cout, p, ldw);
+  return conv1x1_tf32_forward(b, cin, cout, (int)p, x, w, ldw, y, shift, sums, (cudaStream_t)stream);
+}
+
+int bqa_conv1x1_tf32_wgrad(int b, int cin, int cout, long long p, const float *x, const float *dy, float *dw,
+                           void *stream) {
+  NONNEG(b); NONNEG(cin); NONNEG(cout);
+  BQA_REQUIRE(p >= 0, "%s: p must be >= 0", __func__);
+  if ((long long)cin * cout == 0) return BQA_OK;
+  PTR(dw);
+  if ((long long)b * p == 0) return BQA_OK;
+  PTR(x); PTR(dy);
+  BQA_REQUIRE((p % 4) == 0 && cout <= 256, "%s: needs p %% 4 == 0 and cout <= 256 (cout=%d p=%lld)", __func__, cout, p);
+  return conv1x1_tf32_wgrad(b, cin, cout, (int)p, x, dy, dw, (cudaStream_t)stream);
 }
 
 int bqa_bn_relu_forward(int b, int c, long long l, const float *y, const float *mean, const float *invstd,

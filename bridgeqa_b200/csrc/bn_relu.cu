@@ -129,6 +129,28 @@ __global__ void bn_finalize_kernel(int c, long long l, double count, const float
   }
 }
 
+// sums = [sum (y - K), sum (y - K)^2] accumulated elsewhere (the conv kernel's epilogue, conv_tf32.cu)
+// around the per-channel shift K = shift[ch] (NULL: 0); shift may alias running_mean (read first)
+__global__ void bn_finalize_shifted_kernel(int c, double count, const double *__restrict__ sums,
+                                           const float *shift, float eps, float momentum,
+                                           float *__restrict__ mean, float *__restrict__ invstd,
+                                           float *running_mean, float *running_var) {
+  const int ch = blockIdx.x * blockDim.x + threadIdx.x;
+  if (ch >= c) return;
+  const double k = shift ? (double)shift[ch] : 0.0;
+  const double ms = sums[ch] / count;
+  double var = sums[c + ch] / count - ms * ms;
+  if (var < 0.0) var = 0.0;
+  const double m = k + ms;
+  mean[ch] = (float)m;
+  invstd[ch] = (float)(1.0 / sqrt(var + (double)eps));
+  if (running_mean) running_mean[ch] = (1.f - momentum) * running_mean[ch] + momentum * (float)m;
+  if (running_var) {
+    const double unbiased = count > 1.0 ? var * count / (count - 1.0) : var;
+    running_var[ch] = (1.f - momentum) * running_var[ch] + momentum * (float)unbiased;
+  }
+}
+
 __global__ void __launch_bounds__(kThreads)
 bn_relu_apply_kernel(int c, long long l, const float *__restrict__ y, const float *__restrict__ mean,
                      const float *__restrict__ invstd, const float *__restrict__ gamma,
@@ -348,6 +370,15 @@ int bn_stats_dispatch(int b, int c, long long l, const float *y, double *sums, f
                                                           mean, invstd, running_mean, running_var);
   count_launch();
   return check_launch("bn_finalize_kernel");
+}
+
+int bn_finalize_shifted_dispatch(int c, double count, const double *sums, const float *shift, float eps,
+                                 float momentum, float *mean, float *invstd, float *running_mean,
+                                 float *running_var, cudaStream_t stream) {
+  bn_finalize_shifted_kernel<<<ceil_div(c, 128), 128, 0, stream>>>(c, count, sums, shift, eps, momentum, mean,
+                                                                  invstd, running_mean, running_var);
+  count_launch();
+  return check_launch("bn_finalize_shifted_kernel");
 }
 
 int bn_relu_apply_dispatch(int b, int c, long long l, const float *y, const float *mean, const float *invstd,

@@ -90,6 +90,8 @@ class _ConvBlock(nn.Sequential):
         plan = self._conv_bn_relu() if (self.training and x.is_cuda) else None
         if plan is not None:
             conv, norm = plan
+            if train_fused.conv_norm_supported(conv, norm, x):
+                return train_fused.conv_bn_relu(x, conv, norm)       # tcgen05 conv + statistics in its epilogue
             y = conv(x)
             if train_fused.norm_supported(norm, y):
                 return train_fused.bn_relu(y, norm)
@@ -104,6 +106,10 @@ class _ConvBlock(nn.Sequential):
         plan = self._conv_bn_relu() if (self.training and x.is_cuda) else None
         if plan is not None:
             conv, norm = plan
+            if (train_fused.conv_norm_supported(conv, norm, x) and x.dim() == 4
+                    and x.shape[0] * conv.out_channels <= 65535
+                    and bool(train_fused.N.lib().bqa_bn_relu_max_supported(int(x.shape[3])))):
+                return train_fused.conv_bn_relu_max(x, conv, norm)
             y = conv(x)
             if train_fused.norm_supported(norm, y) and train_fused.max_supported(y):
                 return train_fused.bn_relu_max(y, norm)

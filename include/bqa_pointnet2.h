@@ -314,6 +314,27 @@ BQA_API int bqa_count_points_in_boxes(int b, int n, int k, const float *xyz, con
  *                            training-mode backward with the ReLU mask recomputed from y
  *   bqa_bn_relu_max_backward: same from dout (b,c,npoint) + argmax                              */
 BQA_API int bqa_bn_relu_max_supported(int nsample);
+/* bqa_bn_finalize_shifted: mean / invstd (+ running-stat update) from sums = [sum (y-K), sum (y-K)^2]
+ * (2*c doubles) accumulated by bqa_conv1x1_tf32_forward around K = shift[ch] (NULL: 0); count = b*l.
+ * shift may be running_mean itself (read before it is updated). */
+BQA_API int bqa_bn_finalize_shifted(int c, double count, const double *sums, const float *shift, float eps,
+                                    float momentum, float *mean, float *invstd, float *running_mean,
+                                    float *running_var, void *stream);
+
+/* ---- 1x1 convolution of a SharedMLP block in training mode (tcgen05, TF32 operands, fp32 accumulate)
+ * replaces the cuDNN calls behind nn.Conv2d / nn.Conv1d (kernel 1, no bias) of
+ * lib/pointnet2/pytorch_utils.py:104-157 and their autograd backward.
+ *   forward: y (b,cout,p) = w (cout, cin; rows ldw floats apart, ldw % 4 == 0) . x (b,cin,p); p % 4 == 0;
+ *            sums (optional, 2*cout doubles, ACCUMULATED into: zero them first) receive the BatchNorm
+ *            batch statistics sum (y - shift[c]), sum (y - shift[c])^2 from the epilogue (shift NULL: 0).
+ *            The data gradient is the same call with w^T (cin, cout) and dy: dx = w^T . dy.
+ *   wgrad:   dw (cout, cin) += sum over b, p of dy[b,:,p] x[b,:,p]^T  (zero dw first; cout <= 256).
+ * All tensors 16-byte aligned. */
+BQA_API int bqa_conv1x1_tf32_supported(int b, int cin, int cout, long long p, int ldw);
+BQA_API int bqa_conv1x1_tf32_forward(int b, int cin, int cout, long long p, const float *x, const float *w,
+                                     int ldw, float *y, const float *shift, double *sums, void *stream);
+BQA_API int bqa_conv1x1_tf32_wgrad(int b, int cin, int cout, long long p, const float *x, const float *dy,
+                                   float *dw, void *stream);
 BQA_API int bqa_bn_train_stats(int b, int c, long long l, const float *y, double *sums_scratch, float eps,
                                float momentum, float *mean, float *invstd, float *running_mean,
                                float *running_var, void *stream);

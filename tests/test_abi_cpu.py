@@ -53,6 +53,36 @@ def test_sass_is_sm100a_and_uses_cluster_and_bulk_copy():
     assert "REDUX" in sass             # redux.sync argmax
     assert "UCGABAR" in sass or "CGABAR" in sass     # barrier.cluster
     assert "STAS" in sass or "ST.ASYNC" in sass.upper() or "STS.ASYNC" in sass.upper(), "st.async missing"
+    # the fused SA / FP layers: tcgen05.mma (kind::f16), TMEM loads, commit -> mbarrier, cp.async gathers
+    assert "UTCHMMA" in sass, "tcgen05.mma missing"
+    assert "LDTM" in sass, "tcgen05.ld missing"
+    assert "UTCBAR" in sass, "tcgen05.commit missing"
+    assert "LDGSTS" in sass, "cp.async missing"
+
+
+def test_sass_histogram_in_profiles_matches_the_built_library():
+    """profiles/r2_sass_histogram.json (tools/sass_histogram.py) is the committed opcode evidence: the
+    kernels the headline rests on must carry their instructions in the library built from this tree."""
+    import json
+    import shutil
+    import sys
+    if not shutil.which("cuobjdump"):
+        pytest.skip("cuobjdump not available")
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import sass_histogram
+    from bridgeqa_b200 import build
+    arch, kernels = sass_histogram.histogram(build.build())
+    assert arch == ["sm_100a"]
+    names = sass_histogram.demangle(list(kernels))
+    by = {n: c for n, c in zip(names, kernels.values())}
+
+    def some(prefix, op):
+        return any(prefix in n and c[op] > 0 for n, c in by.items())
+    assert some("sa_v2_kernel", "UTCHMMA") and some("sa_v2_kernel", "LDTM") and some("sa_v2_kernel", "LDGSTS")
+    assert some("fp_mlp_kernel", "UTCHMMA") and some("fp_mlp_kernel", "LDTM") and some("fp_mlp_kernel", "UBLKCP")
+    assert some("fps_sorted_kernel", "STAS") and some("fps_stream_kernel", "CREDUX")
+    committed = json.load(open(os.path.join(ROOT, "profiles", "r2_sass_histogram.json")))
+    assert committed["arch"] == ["sm_100a"] and committed["totals"]["UTCHMMA"] > 0 and committed["totals"]["LDTM"] > 0
 
 
 def test_invalid_arguments_return_status_and_message_without_a_gpu():
