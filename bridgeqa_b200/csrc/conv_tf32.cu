@@ -39,7 +39,7 @@ namespace {
 
 constexpr int kTileN = 128;      // positions per forward tile
 constexpr int kKC = 32;          // K per pipeline stage: 32 fp32 = one 128-byte swizzle row
-constexpr int kStages = 4;
+constexpr int kMaxStages = 12;   // ring depth is chosen per launch: as many stages as shared memory holds
 constexpr int kThreads = 192;    // warp 0: TMA producer, warp 1: MMA issuer, warps 2-5: epilogue
 
 // ---- tensor maps (host) -------------------------------------------------------------------
@@ -64,14 +64,14 @@ EncodeTiledFn encode_fn() {
 // (16-byte chunks, or 32-byte chunks for `atom32`: the only swizzle an MN-major TF32 operand may
 // have); out-of-bounds elements read as zero
 int make_map(CUtensorMap *tm, const void *base, long long d0, long long d1, long long d2, long long stride1,
-             long long stride2, int b0, int b1, bool atom32 = false) {
+             long long stride2, int b0, int b1, bool atom32 = false, bool plain_f32 = false) {
   EncodeTiledFn fn = encode_fn();
   if (!fn) return set_error(BQA_ERR_CUDA, "cuTensorMapEncodeTiled is not available from this driver");
   cuuint64_t dims[3] = {(cuuint64_t)d0, (cuuint64_t)d1, (cuuint64_t)d2};
   cuuint64_t strides[2] = {(cuuint64_t)stride1 * 4, (cuuint64_t)stride2 * 4};
   cuuint32_t box[3] = {(cuuint32_t)b0, (cuuint32_t)b1, 1u};
   cuuint32_t estr[3] = {1u, 1u, 1u};
-  const CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_TFLOAT32, 3, const_cast<void *>(base), dims, strides, box, estr,
+  const CUresult r = fn(tm, plain_f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_TFLOAT32, 3, const_cast<void *>(base), dims, strides, box, estr,
                         CU_TENSOR_MAP_INTERLEAVE_NONE,
                         atom32 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
                         CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -104,6 +104,16 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap *tm,
       ::"r"(dst), "l"(tm), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
       : "memory");
 }
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap *tm, uint32_t src, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.tile.bulk_group [%0, {%2, %3, %4}], [%1];"
+               ::"l"(tm), "r"(src), "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void bulk_wait_read() {
+  asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
 __device__ __forceinline__ void prefetch_map(const CUtensorMap *tm) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(tm) : "memory");
 }
@@ -133,7 +143,7 @@ __device__ __forceinline__ void mma_tf32(uint32_t d_tmem, uint64_t a_desc, uint6
 }
 
 struct Bars {
-  uint64_t full[kStages], empty[kStages], acc_full[2], acc_empty[2];
+  uint64_t full[kMaxStages], empty[kMaxStages], acc_full[2], acc_empty[2];
 };
 
 // ---- forward / dgrad ----------------------------------------------------------------------------
@@ -142,21 +152,24 @@ struct ConvParams {
   int rows;                      // output channels of one CTA slab, padded: 128 or 256
   int nchunks;                   // ceil(cin / 32)
   int tiles_per_scene, num_tiles;
+  int nstages;                   // ring depth
   float *y;                      // (b, cout, p)
   const float *shift;            // per-channel shift of the statistics (or NULL: 0)
   double *sums;                  // [2 * cout]: sum (y - shift), sum (y - shift)^2; or NULL
   float *dbg;                    // developer builds: first stage of the first tile is dumped here
+  int flags;                     // measurement only (BQA_CONV_FLAGS): 1 = no stores, 2 = no statistics
 };
 
 __global__ void __launch_bounds__(kThreads, 1)
 conv1x1_tf32_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_w,
-                    const ConvParams P) {
+                    const __grid_constant__ CUtensorMap tm_y, const ConvParams P) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // 1024-byte alignment for the 128-byte swizzle atoms
   uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const uint32_t w_bytes = (uint32_t)P.rows * 128u;            // W chunk: rows x 32 tf32
   const uint32_t x_bytes = kTileN * kKC * 4;                   // X chunk: 4 blocks of [32 ch][32 pos]
   const uint32_t stage_bytes = w_bytes + x_bytes;
+  const uint32_t nst = (uint32_t)P.nstages;
   __shared__ Bars bars;
   __shared__ uint32_t s_tmem;
 
@@ -166,11 +179,12 @@ conv1x1_tf32_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_const
   const uint32_t smem_base = smem_u32(smem);
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < kStages; ++s) { mbar_init(smem_u32(&bars.full[s]), 1); mbar_init(smem_u32(&bars.empty[s]), 1); }
+    for (int s = 0; s < kMaxStages; ++s) { mbar_init(smem_u32(&bars.full[s]), 1); mbar_init(smem_u32(&bars.empty[s]), 1); }
     for (int a = 0; a < 2; ++a) { mbar_init(smem_u32(&bars.acc_full[a]), 1); mbar_init(smem_u32(&bars.acc_empty[a]), 128); }
     fence_mbar_init_cluster();
     prefetch_map(&tm_x);
     prefetch_map(&tm_w);
+    prefetch_map(&tm_y);
   }
   if (warp == 1) umma::tmem_alloc(smem_u32(&s_tmem), 512);
   umma::fence_before_sync();
@@ -186,7 +200,7 @@ conv1x1_tf32_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_const
         const int scene = tile / P.tiles_per_scene;
         const int p0 = (tile % P.tiles_per_scene) * kTileN;
         for (int c = 0; c < P.nchunks; ++c, ++g) {
-          const uint32_t s = g % kStages, u = g / kStages;
+          const uint32_t s = g % nst, u = g / nst;
           wait_bar(smem_u32(&bars.empty[s]), (u & 1) ^ 1, 1);   // a fresh barrier passes a wait on parity 1
           const uint32_t full = smem_u32(&bars.full[s]);
           mbar_arrive_expect_tx(full, stage_bytes);
@@ -202,6 +216,11 @@ conv1x1_tf32_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_const
     // ---- MMA issuer ---------------------------------------------------------------------------
     if (lane == 0) {
       const uint32_t idesc = idesc_tf32(128, kTileN, 1);
+      // A (W chunk): K-major, 16-byte-chunk swizzle, 8-row groups 1024 B apart.  B (X chunk): MN-major,
+      // 32-byte-chunk swizzle (atoms of 4 channel rows x 128 B): 32-position blocks 4096 B apart (LBO),
+      // 4-channel groups 512 B apart (SBO)
+      const uint64_t ad0 = desc_sw128(smem_base, 16, 1024);
+      const uint64_t bd0 = desc_sw128(smem_base + w_bytes, kKC * 128, 512, 1);
       uint32_t g = 0, it = 0;
       for (int tile = blockIdx.x; tile < P.num_tiles; tile += gridDim.x, ++it) {
         const uint32_t a = it & 1, ua = it >> 1;
@@ -209,25 +228,24 @@ conv1x1_tf32_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_const
         umma::fence_after_sync();
         const uint32_t d0 = tmem + a * 256;
         for (int c = 0; c < P.nchunks; ++c, ++g) {
-          const uint32_t s = g % kStages, u = g / kStages;
+          const uint32_t s = g % nst, u = g / nst;
           wait_bar(smem_u32(&bars.full[s]), u & 1, 3);
           umma::fence_after_sync();
-          const uint32_t ws = smem_base + s * stage_bytes, xs = ws + w_bytes;
           if (P.dbg && g == 0 && blockIdx.x == 0 && blockIdx.y == 0) {
             const float *wsp = reinterpret_cast<const float *>(smem + s * stage_bytes);
             for (int i = 0; i < 1024; ++i) P.dbg[i] = wsp[i];
             for (int i = 0; i < 1024; ++i) P.dbg[1024 + i] = wsp[w_bytes / 4 + i];
           }
+          // descriptors of this stage = stage-0 descriptors + (s * stage_bytes) >> 4 in the address field
+          const uint64_t ad_s = ad0 + (uint64_t)(s * (stage_bytes >> 4));
+          const uint64_t bd_s = bd0 + (uint64_t)(s * (stage_bytes >> 4));
 #pragma unroll
           for (int k = 0; k < kKC / 8; ++k) {
-            // B: 8 channels x 128 positions, MN-major, 32-byte-chunk swizzle (atoms of 4 channel rows x
-            // 128 B): 32-position blocks 4096 B apart (LBO), 4-channel groups 512 B apart (SBO)
-            const uint64_t bd = desc_sw128(xs + k * 1024, kKC * 128, 512, 1);
-            for (int h = 0; h < halves; ++h) {
-              // A: 128 channels x 8 tf32 (32 B of every 128-byte row), K-major: 8-row groups 1024 B apart
-              const uint64_t ad = desc_sw128(ws + h * (128 * 128) + k * 32, 16, 1024);
-              mma_tf32(d0 + h * 128, ad, bd, idesc, (c | k) != 0);
-            }
+            // A: 128 channels x 8 tf32 = 32 B of every 128-byte row (+2 per k-step); second half 16 KB on.
+            // B: 8 channels x 128 positions = 8 rows of every 32-position block (+1024 B per k-step)
+            mma_tf32(d0, ad_s + (uint64_t)(2 * k), bd_s + (uint64_t)(64 * k), idesc, (c | k) != 0);
+            if (halves == 2)
+              mma_tf32(d0 + 128, ad_s + (uint64_t)(2 * k + (128 * 128 >> 4)), bd_s + (uint64_t)(64 * k), idesc, (c | k) != 0);
           }
           umma::commit(smem_u32(&bars.empty[s]));              // stage reusable once these MMAs have read it
         }
@@ -240,6 +258,9 @@ conv1x1_tf32_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_const
     const uint32_t lane_addr = (uint32_t)(quarter * 32) << 16;
     double s1[2] = {0.0, 0.0}, s2[2] = {0.0, 0.0};
     float shift[2] = {0.f, 0.f};
+    // two 4 KB staging tiles per epilogue warp, behind the ring
+    const uint32_t stage_out = smem_base + nst * stage_bytes + (uint32_t)(warp - 2) * 8192u;
+    int buf = 0;
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
       const int co = slab * 256 + h * 128 + quarter * 32 + lane;
@@ -256,31 +277,48 @@ conv1x1_tf32_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_const
       for (int h = 0; h < 2; ++h) {
         if (h >= halves) break;
         const int co = slab * 256 + h * 128 + quarter * 32 + lane;
-        float *row = P.y + ((size_t)scene * P.cout + (co < P.cout ? co : 0)) * P.p + p0;
         float t1 = 0.f, t2 = 0.f;
 #pragma unroll 1
         for (int c0 = 0; c0 < kTileN; c0 += 32) {
           uint32_t v[32];
           umma::ld_32x32b_x32(tmem + lane_addr + a * 256 + h * 128 + c0, v);
           umma::wait_ld();
-          if (co < P.cout) {
-            if (p0 + c0 + 32 <= P.p) {
+          // y: this warp's 32 channels x 32 positions go through a swizzled staging tile (row = channel,
+          // 128 B) and one TMA store, which also clips channels >= cout and positions >= p
+          if (!(P.flags & 1)) {
+            if (lane == 0) bulk_wait_read<1>();                 // the store that last read this buffer is done
+            __syncwarp();
+            const uint32_t tile_s = stage_out + (uint32_t)buf * 4096u;
 #pragma unroll
-              for (int q = 0; q < 8; ++q)
-                *reinterpret_cast<float4 *>(row + c0 + 4 * q) =
-                    make_float4(__uint_as_float(v[4 * q]), __uint_as_float(v[4 * q + 1]),
-                                __uint_as_float(v[4 * q + 2]), __uint_as_float(v[4 * q + 3]));
+            for (int q = 0; q < 8; ++q)
+              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};"
+                           ::"r"(tile_s + (uint32_t)lane * 128u + (uint32_t)((q ^ (lane & 7)) * 16)), "r"(v[4 * q]),
+                             "r"(v[4 * q + 1]), "r"(v[4 * q + 2]), "r"(v[4 * q + 3])
+                           : "memory");
+            umma::fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) {
+              tma_store_3d(&tm_y, tile_s, p0 + c0, slab * 256 + h * 128 + quarter * 32, scene);
+              bulk_commit();
+            }
+            buf ^= 1;
+          }
+          if (co < P.cout && !(P.flags & 2)) {
+            if (p0 + c0 + 32 <= P.p) {
+              // four independent chains per sum (a 32-long dependent chain would cost ~130 cycles)
+              float a1[4] = {0.f, 0.f, 0.f, 0.f}, a2[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
               for (int e = 0; e < 32; ++e) {
                 const float d = __uint_as_float(v[e]) - shift[h];
-                t1 += d;
-                t2 = fmaf(d, d, t2);
+                a1[e & 3] += d;
+                a2[e & 3] = fmaf(d, d, a2[e & 3]);
               }
+              t1 += (a1[0] + a1[1]) + (a1[2] + a1[3]);
+              t2 += (a2[0] + a2[1]) + (a2[2] + a2[3]);
             } else {
               for (int e = 0; e < 32; ++e) {
                 if (p0 + c0 + e < P.p) {
                   const float d = __uint_as_float(v[e]) - shift[h];
-                  row[c0 + e] = __uint_as_float(v[e]);
                   t1 += d;
                   t2 = fmaf(d, d, t2);
                 }
@@ -294,6 +332,7 @@ conv1x1_tf32_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_const
       umma::fence_before_sync();
       mbar_arrive(smem_u32(&bars.acc_empty[a]));
     }
+    if (lane == 0) bulk_wait_read<0>();                         // staging tiles are read before the CTA exits
     if (P.sums) {
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
@@ -318,7 +357,7 @@ struct WgradParams {
   int steps_per_scene;           // ceil(p / 32)
   long long total_steps;         // b * steps_per_scene
   int splits;                    // gridDim.x
-  int nstages;                   // ring depth that fits shared memory (3 or 4)
+  int nstages;                   // ring depth
   float *dw;                     // (cout, cin), accumulated with red.add
 };
 
@@ -343,7 +382,7 @@ wgrad_tf32_kernel(const __grid_constant__ CUtensorMap tm_dy, const __grid_consta
   const long long st1 = st0 + per < P.total_steps ? st0 + per : P.total_steps;
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < kStages; ++s) { mbar_init(smem_u32(&bars.full[s]), 1); mbar_init(smem_u32(&bars.empty[s]), 1); }
+    for (int s = 0; s < kMaxStages; ++s) { mbar_init(smem_u32(&bars.full[s]), 1); mbar_init(smem_u32(&bars.empty[s]), 1); }
     mbar_init(smem_u32(&bars.acc_full[0]), 1);
     fence_mbar_init_cluster();
     prefetch_map(&tm_dy);
@@ -378,19 +417,21 @@ wgrad_tf32_kernel(const __grid_constant__ CUtensorMap tm_dy, const __grid_consta
   } else if (warp == 1) {
     if (lane == 0) {
       const uint32_t idesc = idesc_tf32(128, P.ncols, 0);
+      const uint64_t ad0 = desc_sw128(smem_base, 16, 1024);              // dy rows: K-major, 8-row groups 1024 B apart
+      const uint64_t bd0 = desc_sw128(smem_base + a_bytes, 16, 1024);    // x rows: the same
       uint32_t g = 0;
       for (long long st = st0; st < st1; ++st, ++g) {
         const uint32_t s = g % nst, u = g / nst;
         wait_bar(smem_u32(&bars.full[s]), u & 1, 13);
         umma::fence_after_sync();
-        const uint32_t as = smem_base + s * stage_bytes, bs = as + a_bytes;
+        const uint64_t ad_s = ad0 + (uint64_t)(s * (stage_bytes >> 4));
+        const uint64_t bd_s = bd0 + (uint64_t)(s * (stage_bytes >> 4));
 #pragma unroll
         for (int k = 0; k < 4; ++k) {                           // 8 positions (32 B of every row) per MMA
-          const uint64_t bd = desc_sw128(bs + k * 32, 16, 1024);
-          for (int h = 0; h < halves; ++h) {
-            const uint64_t ad = desc_sw128(as + h * (128 * 128) + k * 32, 16, 1024);
-            mma_tf32(tmem + h * 256, ad, bd, idesc, (g | (uint32_t)k) != 0);
-          }
+          mma_tf32(tmem, ad_s + (uint64_t)(2 * k), bd_s + (uint64_t)(2 * k), idesc, (g | (uint32_t)k) != 0);
+          if (halves == 2)
+            mma_tf32(tmem + 256, ad_s + (uint64_t)(2 * k + (128 * 128 >> 4)), bd_s + (uint64_t)(2 * k), idesc,
+                     (g | (uint32_t)k) != 0);
         }
         umma::commit(smem_u32(&bars.empty[s]));
       }
@@ -452,6 +493,8 @@ int conv1x1_tf32_forward(int b, int cin, int cout, int p, const float *x, const 
   P.num_tiles = b * P.tiles_per_scene;
   P.y = y; P.shift = shift; P.sums = sums;
   P.dbg = nullptr;
+  static const int flags = [] { const char *e = getenv("BQA_CONV_FLAGS"); return e ? atoi(e) : 0; }();
+  P.flags = flags;
   if (const char *e = getenv("BQA_CONV_DEBUG")) {
     static float *dbg = nullptr;
     if (!dbg) cudaMalloc(&dbg, 2048 * sizeof(float));
@@ -460,11 +503,16 @@ int conv1x1_tf32_forward(int b, int cin, int cout, int p, const float *x, const 
   CUtensorMap tm_x, tm_w;
   if (int rc = make_map(&tm_x, x, p, cin, b, p, (long long)cin * p, 32, kKC, true)) return rc;
   if (int rc = make_map(&tm_w, w, cin, cout, 1, ldw, (long long)cout * ldw, kKC, P.rows)) return rc;
-  const size_t smem = (size_t)kStages * (P.rows * 128 + kTileN * kKC * 4) + 1024;
+  CUtensorMap tm_y;
+  if (int rc = make_map(&tm_y, y, p, cout, b, p, (long long)cout * p, 32, 32, false, true)) return rc;
+  const size_t stage = (size_t)P.rows * 128 + kTileN * kKC * 4;
+  P.nstages = (int)((size_t)(226 * 1024 - 4 * 8192 - 1024) / stage);
+  if (P.nstages > kMaxStages) P.nstages = kMaxStages;
+  const size_t smem = P.nstages * stage + 4 * 8192 + 1024;
   BQA_CUDA(cudaFuncSetAttribute(conv1x1_tf32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int slabs = ceil_div(cout, 256);
   dim3 grid((unsigned)min(P.num_tiles, max(1, sm_count() / slabs)), (unsigned)slabs);
-  conv1x1_tf32_kernel<<<grid, kThreads, smem, stream>>>(tm_x, tm_w, P);
+  conv1x1_tf32_kernel<<<grid, kThreads, smem, stream>>>(tm_x, tm_w, tm_y, P);
   if (P.dbg) {
     static float host[2048];
     cudaMemcpy(host, P.dbg, sizeof(host), cudaMemcpyDeviceToHost);
@@ -500,7 +548,8 @@ int conv1x1_tf32_wgrad(int b, int cin, int cout, int p, const float *x, const fl
   if (int rc = make_map(&tm_dy, dy, p, cout, b, p, (long long)cout * p, 32, P.rows)) return rc;
   if (int rc = make_map(&tm_x, x, p, cin, b, p, (long long)cin * p, 32, P.ncols)) return rc;
   const size_t stage = (size_t)(P.rows + P.ncols) * 128;
-  P.nstages = stage * 4 <= 200 * 1024 ? 4 : 3;
+  P.nstages = (int)((size_t)(226 * 1024 - 1024) / stage);
+  if (P.nstages > kMaxStages) P.nstages = kMaxStages;
   const size_t smem = P.nstages * stage + 1024;
   BQA_CUDA(cudaFuncSetAttribute(wgrad_tf32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   dim3 grid((unsigned)P.splits, (unsigned)slabs);
