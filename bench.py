@@ -198,6 +198,12 @@ def algorithmic_work(name, dims):
     if name == "bqa_bn_train_stats":
         b, c, l = dims[:3]
         return {"bytes": 4 * b * c * l, "bound": "hbm"}
+    if name == "bqa_conv1x1_tf32_forward":        # read x, write y (the weights stay in L2); HBM-bound
+        b, cin, cout, p = dims[:4]
+        return {"bytes": 4 * b * p * (cin + cout), "flops": 2 * b * p * cin * cout, "bound": "hbm"}
+    if name == "bqa_conv1x1_tf32_wgrad":          # read x and dy once
+        b, cin, cout, p = dims[:4]
+        return {"bytes": 4 * b * p * (cin + cout), "flops": 2 * b * p * cin * cout, "bound": "hbm"}
     if name == "bqa_bn_relu_forward":
         b, c, l = dims[:3]
         return {"bytes": 8 * b * c * l, "bound": "hbm"}
@@ -275,19 +281,23 @@ def sms_occupied(name, dims, sms=148):
     return None
 
 
-def run_train_mode(args, torch, dist, device, world, rank, real_stdout):
-    """configs[3]: fwd + bwd + gradient all-reduce of the detector (C = 132), train-mode BN."""
-    from bridgeqa_b200 import _native, detector, synthetic, training
+def measure_train(args, torch, dist, device, world, rank, steps, warmup, per_kernel=True, sample_clocks=True):
+    """configs[3]: K training steps of the detector (C = 132, train-mode BN): fwd + bwd + gradient
+    all-reduce (launched bucket by bucket from inside the backward pass when world > 1).  Returns the
+    measurements as a dict (device time, max over ranks)."""
+    from bridgeqa_b200 import _native, detector, distributed as D, fused as _fused, synthetic, training
     feats = 132
     net = synthetic.fill_state_dict(detector.VoteNetDetector(feats), seed=0).to(device)
     loss_fn = training.ProjectionLoss().to(device)
     bsz = args.train_batch
     pc = synthetic.make_batch(bsz, NUM_POINTS, feats, first_scene=rank * bsz).to(device)
+    old_tf32 = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
     torch.backends.cudnn.allow_tf32 = True          # torch's (and the reference's) default
     torch.backends.cuda.matmul.allow_tf32 = True
+    from bridgeqa_b200 import train_fused
     if args.torch_bn:
-        from bridgeqa_b200 import train_fused
         train_fused.set_enabled(False)
+    reducer = D.OverlappedGradReducer(net) if world > 1 else None
 
     def barrier():
         torch.cuda.synchronize()
@@ -297,41 +307,76 @@ def run_train_mode(args, torch, dist, device, world, rank, real_stdout):
 
     # the next batch's SA1 sampling (coordinates only) is issued under this step's backward
     nxt = None if args.no_prefetch else pc
-    from bridgeqa_b200 import fused as _fused
-    clocks = ClockSampler(int(os.environ.get("LOCAL_RANK", "0")))
-    if rank == 0:
+    clocks = ClockSampler(int(os.environ.get("LOCAL_RANK", "0"))) if sample_clocks else None
+    if rank == 0 and clocks:
         clocks.start()
-    for _ in range(args.warmup):
-        training.train_step(net, loss_fn, pc, next_point_clouds=nxt)
+    for _ in range(warmup):
+        training.train_step(net, loss_fn, pc, next_point_clouds=nxt, reducer=reducer)
     barrier()
     l0 = _native.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    clocks.mark_begin()
+    if clocks:
+        clocks.mark_begin()
     e0.record()
-    for _ in range(args.steps):
-        loss = training.train_step(net, loss_fn, pc, next_point_clouds=nxt)
+    for _ in range(steps):
+        loss = training.train_step(net, loss_fn, pc, next_point_clouds=nxt, reducer=reducer)
     # K steps = K samplings inside the timed region: the first consumed the warm-up's prefetch,
     # the last one's prefetch has to finish before the clock stops
     torch.cuda.current_stream(device).wait_stream(_fused.side_stream(device, "prefetch"))
     e1.record()
     barrier()
-    clocks.mark_end()
-    clk = clocks.stop() if rank == 0 else None
+    clk = None
+    if clocks:
+        clocks.mark_end()
+        clk = clocks.stop() if rank == 0 else None
     t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=device)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms = float(t[0])
     launches = _native.launch_count() - l0
-    # per-kernel pass (one more step, CUDA events around every C-ABI call)
-    from bridgeqa_b200 import profiler
-    with profiler.KernelTimer() as kt:
-        k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        k0.record()
-        training.train_step(net, loss_fn, pc)
-        k1.record()
-        barrier()
-    kern = kt.summary()
-    kpass_ms = k0.elapsed_time(k1)
+    # the exchange alone: the reducer's buckets, all-reduced back to back (what the backward pass hides)
+    ar_ms, ar_bytes = 0.0, 0
+    if reducer is not None:
+        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        for rep in range(3):
+            if rep == 1:
+                torch.cuda.synchronize()
+                a0.record()
+            for flat, _members in reducer.buckets:
+                dist.all_reduce(flat, op=dist.ReduceOp.AVG)
+        a1.record()
+        torch.cuda.synchronize()
+        ar_ms = a0.elapsed_time(a1) / 2.0
+        ar_bytes = reducer.bytes
+    nparam = sum(p.numel() for p in net.parameters())
+    res = {"ms": ms, "steps": steps, "warmup": warmup, "launches": launches, "loss": float(loss), "clk": clk,
+           "bsz": bsz, "nparam": nparam, "allreduce_ms": ar_ms, "allreduce_bytes": ar_bytes,
+           "conv": "tcgen05 TF32 (conv_tf32.cu)" if train_fused.conv_enabled() else "cuDNN TF32",
+           "fused_bn_relu": bool(train_fused.enabled())}
+    if per_kernel:
+        # per-kernel pass (one more step, CUDA events around every C-ABI call)
+        from bridgeqa_b200 import profiler
+        with profiler.KernelTimer() as kt:
+            k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            k0.record()
+            training.train_step(net, loss_fn, pc, reducer=reducer)
+            k1.record()
+            barrier()
+        res["kern"] = kt.summary()
+        res["kpass_ms"] = k0.elapsed_time(k1)
+    torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old_tf32
+    if args.torch_bn:
+        train_fused.set_enabled(True)
+    del net, pc, reducer
+    torch.cuda.empty_cache()
+    return res
+
+
+def run_train_mode(args, torch, dist, device, world, rank, real_stdout):
+    """--mode train: the configs[3] line on its own."""
+    res = measure_train(args, torch, dist, device, world, rank, args.steps, args.warmup)
+    ms, kern, kpass_ms, bsz, nparam, clk, launches, loss = (res["ms"], res["kern"], res["kpass_ms"], res["bsz"],
+                                                            res["nparam"], res["clk"], res["launches"], res["loss"])
     if rank == 0:
         peaks = measured_peaks()
         groups = {}
@@ -358,13 +403,15 @@ def run_train_mode(args, torch, dist, device, world, rank, real_stdout):
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "tf32",
                 "data": "synthetic",
                 "config": {"workload": "VoteNetDetector fwd+bwd, train-mode BN, %d scenes/GPU: sm_100a operators "
-                                       "(sampling, grid ball query, grouping, BatchNorm+ReLU+max fwd/bwd) + cuDNN "
-                                       "TF32 1x1 convs, one flat NCCL all-reduce of %d fp32 gradients" % (bsz, nparam),
-                           "fused_bn_relu": bool(__import__("bridgeqa_b200.train_fused", fromlist=["x"]).enabled()),
+                                       "(sampling, grid ball query, grouping, 1x1 convs, BatchNorm+ReLU+max "
+                                       "fwd/bwd), NCCL all-reduce of %d fp32 gradients in 2 buckets launched "
+                                       "from the backward pass" % (bsz, nparam),
+                           "convs": res["conv"], "fused_bn_relu": res["fused_bn_relu"],
                            "sampling_prefetch": not args.no_prefetch},
+                "allreduce": {"ms_alone": round(res["allreduce_ms"], 4), "bytes": res["allreduce_bytes"]},
                 "clocks": clk,
                 "kernels": kernels, "kernel_pass_ms": round(kpass_ms, 3),
-                "gpu_launches": launches, "loss": float(loss)}
+                "gpu_launches": launches, "loss": loss}
         sys.stdout.flush()
         os.dup2(real_stdout, 1)
         print(json.dumps(line), flush=True)
@@ -411,6 +458,9 @@ def main():
                          "on the HOST needs (seed coordinates / indices + per-scene feature checksum; the seed "
                          "features are consumed on the device by voting / proposal); features16 / features32 add "
                          "fp2_features as fp16 / fp32")
+    ap.add_argument("--no-train", action="store_true", help="skip the `train` block (configs[3]: a few DET training "
+                    "steps of the C=132 detector, fwd + bwd + gradient all-reduce) of the default line")
+    ap.add_argument("--train-steps", type=int, default=5, help="timed steps of the `train` block (2 warm-up steps)")
     ap.add_argument("--no-ref-ext", action="store_true", help="skip the `ref_ext` leg (stock reference modules on the "
                     "reference's own CUDA extension, timed in a subprocess on the same GPU)")
     ap.add_argument("--precision", default="fp16", choices=["fp16", "bf16"],
@@ -641,6 +691,14 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     elapsed_ms, e2e_ms, serial_ms = float(t[0]), float(t[1]), float(t[3])
 
+    # configs[3] in the same line: a few training steps on every rank (the all-reduce is a collective)
+    train_res = None
+    if not args.no_train and args.workload == "backbone" and args.train_steps > 0:
+        try:
+            train_res = measure_train(args, torch, dist, device, world, rank, args.train_steps, 2,
+                                      per_kernel=False, sample_clocks=False)
+        except Exception as e:       # the forward line must survive a failing extra
+            train_res = {"error": repr(e)[:300]}
     if rank == 0:
         peaks = measured_peaks()
         scenes = BATCH * world * args.steps
@@ -678,7 +736,7 @@ def main():
                 else "r1_kernels_ncu.json"
             prof = json.load(open(os.path.join(ROOT, "profiles", prof_name)))
             names = {"bqa_furthest_point_sampling": "fps_cluster_kernel<14", "bqa_furthest_point_sampling_grid": "fps_sorted_kernel<14",
-                     "bqa_furthest_point_sampling_grid_lean": "fps_sorted_kernel<18, 768"}
+                     "bqa_furthest_point_sampling_grid_lean": "fps_stream_kernel"}
             if top and top["kernel"] in names and top["dims"][:3] == [BATCH, NUM_POINTS, 2048]:
                 hit = [k for k in prof if k["kernel"].startswith(names[top["kernel"]])]
                 if hit:
@@ -752,6 +810,23 @@ def main():
             "note": "timed regime: ms_per_step x 148 SMs; rows = SMs held x kernel duration for the kernels that "
                     "hold whole SMs (sampling clusters, persistent SA / FP CTAs); the rest are short kernels",
             "kernels": sorted(budget, key=lambda r_: -r_["sm_ms"])}
+        if train_res is not None:
+            if "error" in train_res:
+                line["train"] = train_res
+            else:
+                tms = train_res["ms"] / train_res["steps"]
+                line["train"] = {
+                    "metric": "scenes/sec DET train step (fwd+bwd+grad all-reduce), 40k pts, C=132 (configs[3])",
+                    "value": train_res["bsz"] * world / (tms / 1e3), "unit": UNIT, "ms_per_step": round(tms, 4),
+                    "steps": train_res["steps"], "warmup": train_res["warmup"], "scenes_per_gpu": train_res["bsz"],
+                    "n_gpus": world, "scaling": "weak", "dtype": "tf32", "convs": train_res["conv"],
+                    "fused_bn_relu": train_res["fused_bn_relu"], "gpu_launches": train_res["launches"],
+                    "allreduce": {"ms_alone": round(train_res["allreduce_ms"], 4), "bytes": train_res["allreduce_bytes"],
+                                  "how": "2 flat fp32 buckets, NCCL all-reduce launched from the backward pass "
+                                         "(distributed.OverlappedGradReducer); ms_alone = the same buckets reduced "
+                                         "back to back outside a step"},
+                    "loss": train_res["loss"],
+                    "note": "device time, max over ranks; eager issue (~900 launches per step)"}
         if world == 1 and not args.no_cpu_baseline:
             r = cpu_reference_run(steps=1, warmup=0, sample_scenes=4)
             line["cpu_baseline"] = {"value": r["value"], "unit": UNIT, "cores": r["cores"],

@@ -28,16 +28,21 @@ class ProjectionLoss(torch.nn.Module):
         return a.pow(2).mean() + b.pow(2).mean() + c.pow(2).mean()
 
 
-def train_step(model, loss_fn, point_clouds, optimizer=None, next_point_clouds=None):
+def train_step(model, loss_fn, point_clouds, optimizer=None, next_point_clouds=None, reducer=None):
     """One fwd + bwd (+ gradient all-reduce when a process group is up, + optimizer step).
     Returns the detached loss.
 
     next_point_clouds: the batch the NEXT call will be given (already on the device).  Its SA1
     sampling -- 1.3 ms of serial chain that depends on coordinates only, not on the weights this
     step updates -- is issued on a side stream before this step's backward and runs underneath it
-    (Pointnet2Backbone.prefetch_sampling); the next forward picks it up."""
+    (Pointnet2Backbone.prefetch_sampling); the next forward picks it up.
+
+    reducer: a distributed.OverlappedGradReducer built once for `model` -- the gradient all-reduce is then
+    launched bucket by bucket from inside the backward pass instead of after it."""
     model.train()
-    if optimizer is not None:
+    if reducer is not None:
+        reducer.prepare()
+    elif optimizer is not None:
         optimizer.zero_grad(set_to_none=True)
     else:
         for p in model.parameters():
@@ -49,7 +54,9 @@ def train_step(model, loss_fn, point_clouds, optimizer=None, next_point_clouds=N
         if hasattr(backbone, "prefetch_sampling"):
             backbone.prefetch_sampling(next_point_clouds)
     loss.backward()
-    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+    if reducer is not None:
+        reducer.finish()
+    elif dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
         D.allreduce_gradients(model)
     if optimizer is not None:
         torch.nn.utils.clip_grad_value_(model.parameters(), 1.0)     # lib/solver.py:409

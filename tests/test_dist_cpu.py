@@ -69,3 +69,51 @@ def test_shard_scenes_partitions():
             assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
             sizes = [e - b for b, e in spans]
             assert max(sizes) - min(sizes) <= 1
+
+
+def _worker_overlap(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from bridgeqa_b200 import detector, distributed as D, synthetic
+    try:
+        torch.manual_seed(0)
+        net = synthetic.fill_state_dict(detector.VotingModule(1, 32), seed=3)
+        ref = synthetic.fill_state_dict(detector.VotingModule(1, 32), seed=3)
+        reducer = D.OverlappedGradReducer(net, nbuckets=3)
+        xyz = torch.randn(2, 16, 3, generator=torch.Generator().manual_seed(10 + rank))
+        feat = torch.randn(2, 32, 16, generator=torch.Generator().manual_seed(20 + rank))
+        launched_during_backward = []
+        for step in range(2):                                  # the second step reuses the buckets
+            reducer.prepare()
+            v, f = net(xyz, feat)
+            (v.sum() + f.pow(2).sum()).backward()
+            launched_during_backward.append(sum(w is not None for w in reducer._works))
+            nbytes = reducer.finish()
+        # reference: local gradients, then the flat-bucket all-reduce of the same module
+        v, f = ref(xyz, feat)
+        (v.sum() + f.pow(2).sum()).backward()
+        D.allreduce_gradients(ref)
+        err = max(float((a.grad - b.grad).abs().max()) for a, b in zip(net.parameters(), ref.parameters()))
+        q.put((rank, nbytes, err, launched_during_backward, len(reducer.buckets)))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_rank_overlapped_gradient_reducer_matches_flat_allreduce():
+    """OverlappedGradReducer: buckets are launched from the backward hooks (all of them before finish()),
+    the result is the mean the blocking flat-bucket all-reduce gives, and the buckets are reusable."""
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker_overlap, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    out = sorted(q.get(timeout=120) for _ in range(world))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank, nbytes, err, launched, nb in out:
+        assert nbytes > 0 and nb >= 2
+        assert err < 1e-5, err
+        assert launched == [nb, nb], launched            # every bucket went out during backward
