@@ -26,6 +26,17 @@
 //   2. warp argmax over the lanes' run records -> one 32-byte post per warp;
 //   3. __syncthreads; every warp folds the posts (double-buffered, so no second barrier).
 // Tie-break exactly as fps_sorted.cu: 27-bit ~tie_key(k) of the reference's pairwise tree.
+//
+// Measured and rejected (B200, 16 x 40k -> 2048; this kernel: 1.22 us per iteration with 20 warps):
+//  * 32 warps, one run at a time: 1.39 us -- the per-iteration fold / box test of every warp is issue-bound;
+//  * 16 warps, two owner slots per lane: 1.73 us -- more serial work on the busiest warp;
+//  * a single-run fast path with a lazily computed tie key (ballot + shuffle instead of the second
+//    redux): 1.58 us;
+//  * a shared-memory WORK LIST (owners only test boxes; ballot -> atomic slot -> every warp takes one
+//    entry, so the ~21 active runs are processed by 21 warps; second CTA barrier, records through shared
+//    memory): bit-exact, 1.30 us with 20 warps, 1.54 us with 32 -- the busiest warp's 2-3 runs are not
+//    what bounds an iteration: with ~4500 warp-instructions per iteration the SM's four schedulers are
+//    ~50 % busy (ncu) and the rest is the dependent chain fold -> box test -> L2 load -> reduce -> post.
 #include <cstdio>
 #include <cstdlib>
 
