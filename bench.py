@@ -297,7 +297,19 @@ def measure_train(args, torch, dist, device, world, rank, steps, warmup, per_ker
     from bridgeqa_b200 import train_fused
     if args.torch_bn:
         train_fused.set_enabled(False)
-    reducer = D.OverlappedGradReducer(net) if world > 1 else None
+    graphed = None
+    if not getattr(args, "train_eager", False) and not args.no_prefetch and not args.torch_bn:
+        # fwd + bwd replayed from two alternating CUDA graphs (the next batch's sampling is produced by the
+        # current replay); the gradient buckets are all-reduced after the replay
+        graphed = training.GraphedTrainStep(net, loss_fn, pc)
+        reducer = graphed.reducer
+    else:
+        reducer = D.OverlappedGradReducer(net) if world > 1 else None
+
+    def one_step(next_pc):
+        if graphed is not None:
+            return graphed(pc, next_pc)
+        return training.train_step(net, loss_fn, pc, next_point_clouds=next_pc, reducer=reducer)
 
     def barrier():
         torch.cuda.synchronize()
@@ -311,7 +323,7 @@ def measure_train(args, torch, dist, device, world, rank, steps, warmup, per_ker
     if rank == 0 and clocks:
         clocks.start()
     for _ in range(warmup):
-        training.train_step(net, loss_fn, pc, next_point_clouds=nxt, reducer=reducer)
+        one_step(nxt)
     barrier()
     l0 = _native.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -319,7 +331,7 @@ def measure_train(args, torch, dist, device, world, rank, steps, warmup, per_ker
         clocks.mark_begin()
     e0.record()
     for _ in range(steps):
-        loss = training.train_step(net, loss_fn, pc, next_point_clouds=nxt, reducer=reducer)
+        loss = one_step(nxt)
     # K steps = K samplings inside the timed region: the first consumed the warm-up's prefetch,
     # the last one's prefetch has to finish before the clock stops
     torch.cuda.current_stream(device).wait_stream(_fused.side_stream(device, "prefetch"))
@@ -334,9 +346,11 @@ def measure_train(args, torch, dist, device, world, rank, steps, warmup, per_ker
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms = float(t[0])
     launches = _native.launch_count() - l0
+    if graphed is not None:
+        launches = graphed.launches_per_step * steps     # kernel nodes of this library the replays re-issue
     # the exchange alone: the reducer's buckets, all-reduced back to back (what the backward pass hides)
     ar_ms, ar_bytes = 0.0, 0
-    if reducer is not None:
+    if reducer is not None and world > 1:
         a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         for rep in range(3):
             if rep == 1:
@@ -351,6 +365,8 @@ def measure_train(args, torch, dist, device, world, rank, steps, warmup, per_ker
     nparam = sum(p.numel() for p in net.parameters())
     res = {"ms": ms, "steps": steps, "warmup": warmup, "launches": launches, "loss": float(loss), "clk": clk,
            "bsz": bsz, "nparam": nparam, "allreduce_ms": ar_ms, "allreduce_bytes": ar_bytes,
+           "issue": ("2 alternating CUDA graphs (training.GraphedTrainStep); buckets all-reduced after the replay"
+                     if graphed is not None else "eager; buckets all-reduced from the backward hooks"),
            "conv": "tcgen05 TF32 (conv_tf32.cu)" if train_fused.conv_enabled() else "cuDNN TF32",
            "fused_bn_relu": bool(train_fused.enabled())}
     if per_kernel:
@@ -359,7 +375,7 @@ def measure_train(args, torch, dist, device, world, rank, steps, warmup, per_ker
         with profiler.KernelTimer() as kt:
             k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             k0.record()
-            training.train_step(net, loss_fn, pc, reducer=reducer)
+            training.train_step(net, loss_fn, pc, reducer=None if graphed is not None else reducer)
             k1.record()
             barrier()
         res["kern"] = kt.summary()
@@ -367,7 +383,7 @@ def measure_train(args, torch, dist, device, world, rank, steps, warmup, per_ker
     torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old_tf32
     if args.torch_bn:
         train_fused.set_enabled(True)
-    del net, pc, reducer
+    del net, pc, reducer, graphed
     torch.cuda.empty_cache()
     return res
 
@@ -396,7 +412,6 @@ def run_train_mode(args, torch, dist, device, world, rank, real_stdout):
                            frac=round(ach / peaks["hbm_gbs"], 4))
             kernels.append(row)
         kernels.sort(key=lambda r: -r["ms"])
-        nparam = sum(p.numel() for p in net.parameters())
         line = {"metric": "scenes/sec DET train step (fwd+bwd+grad all-reduce), 40k pts, C=132",
                 "value": bsz * world * args.steps / (ms / 1e3), "unit": UNIT, "n_gpus": world,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
@@ -406,7 +421,7 @@ def run_train_mode(args, torch, dist, device, world, rank, real_stdout):
                                        "(sampling, grid ball query, grouping, 1x1 convs, BatchNorm+ReLU+max "
                                        "fwd/bwd), NCCL all-reduce of %d fp32 gradients in 2 buckets launched "
                                        "from the backward pass" % (bsz, nparam),
-                           "convs": res["conv"], "fused_bn_relu": res["fused_bn_relu"],
+                           "convs": res["conv"], "fused_bn_relu": res["fused_bn_relu"], "issue": res["issue"],
                            "sampling_prefetch": not args.no_prefetch},
                 "allreduce": {"ms_alone": round(res["allreduce_ms"], 4), "bytes": res["allreduce_bytes"]},
                 "clocks": clk,
@@ -460,6 +475,8 @@ def main():
                          "fp2_features as fp16 / fp32")
     ap.add_argument("--no-train", action="store_true", help="skip the `train` block (configs[3]: a few DET training "
                     "steps of the C=132 detector, fwd + bwd + gradient all-reduce) of the default line")
+    ap.add_argument("--train-eager", action="store_true", help="issue the training step launch by launch (gradient "
+                    "all-reduce from the backward hooks) instead of replaying training.GraphedTrainStep")
     ap.add_argument("--train-steps", type=int, default=5, help="timed steps of the `train` block (2 warm-up steps)")
     ap.add_argument("--no-ref-ext", action="store_true", help="skip the `ref_ext` leg (stock reference modules on the "
                     "reference's own CUDA extension, timed in a subprocess on the same GPU)")
@@ -821,12 +838,13 @@ def main():
                     "steps": train_res["steps"], "warmup": train_res["warmup"], "scenes_per_gpu": train_res["bsz"],
                     "n_gpus": world, "scaling": "weak", "dtype": "tf32", "convs": train_res["conv"],
                     "fused_bn_relu": train_res["fused_bn_relu"], "gpu_launches": train_res["launches"],
+                    "issue": train_res["issue"],
                     "allreduce": {"ms_alone": round(train_res["allreduce_ms"], 4), "bytes": train_res["allreduce_bytes"],
                                   "how": "2 flat fp32 buckets, NCCL all-reduce launched from the backward pass "
                                          "(distributed.OverlappedGradReducer); ms_alone = the same buckets reduced "
                                          "back to back outside a step"},
                     "loss": train_res["loss"],
-                    "note": "device time, max over ranks; eager issue (~900 launches per step)"}
+                    "note": "device time, max over ranks"}
         if world == 1 and not args.no_cpu_baseline:
             r = cpu_reference_run(steps=1, warmup=0, sample_scenes=4)
             line["cpu_baseline"] = {"value": r["value"], "unit": UNIT, "cores": r["cores"],

@@ -82,6 +82,7 @@ class OverlappedGradReducer(object):
         self._pending = [0] * len(self.buckets)
         self._works = [None] * len(self.buckets)
         self._armed = False
+        self.defer = False          # True: hooks only count; finish() launches (CUDA-graph capture of the step)
         self.bytes = 4 * total
         self._avg = self.world > 1 and dist.get_backend(group) == "nccl"
         for p in self.params:
@@ -116,8 +117,15 @@ class OverlappedGradReducer(object):
             return
         bi = self._bucket_of[id(p)]
         self._pending[bi] -= 1
-        if self._pending[bi] == 0:
+        if self._pending[bi] == 0 and not self.defer:
             self._launch(bi)
+
+    def attach(self):
+        """point every .grad into the buckets without zeroing them (after a graph replay wrote them)"""
+        for flat, members in self.buckets:
+            for p, off in members:
+                p.grad = flat[off:off + p.numel()].view_as(p)
+        self._works = [None] * len(self.buckets)
 
     def finish(self):
         """-> bytes reduced; every .grad then holds the mean over the ranks"""

@@ -190,3 +190,38 @@ def test_detector_train_step_runs_on_the_tcgen05_convolutions():
     rm_a = net_a.detection_backbone.sa2.mlp_module.layer1.bn.bn.running_mean
     rm_b = net_b.detection_backbone.sa2.mlp_module.layer1.bn.bn.running_mean
     torch.testing.assert_close(rm_a, rm_b, rtol=2e-2, atol=2e-3)
+
+
+def test_graphed_train_step_equals_eager_steps():
+    """training.GraphedTrainStep (two alternating CUDA graphs, the next batch's sampling produced by the
+    current replay) against the same steps issued eagerly: loss, gradients and BatchNorm running statistics
+    over four steps that alternate between batches, announced and unannounced.  Backbone only: the detector's
+    vote aggregation re-samples PREDICTED coordinates, where a 1e-6 difference (library algorithm choice
+    under capture) can pick another vote."""
+    from bridgeqa_b200 import detector, synthetic, training
+    old = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = True
+    try:
+        nets = []
+        for _ in range(2):
+            torch.manual_seed(0)
+            nets.append(synthetic.fill_state_dict(detector.Pointnet2Backbone(input_feature_dim=7), seed=6).cuda())
+        w = torch.randn(256, 1024, device="cuda") / 32.0
+
+        def loss_fn(out):
+            return (out["fp2_features"] * w).pow(2).mean() + out["sa4_features"].pow(2).mean()
+        batches = [synthetic.make_batch(2, 5000, 7, first_scene=40 + 2 * i).cuda() for i in range(3)]
+        order = [0, 1, 2, 1]
+        graphed = training.GraphedTrainStep(nets[0], loss_fn, batches[0])
+        for step, bi in enumerate(order):
+            nxt = batches[order[step + 1]] if step + 1 < len(order) and step != 1 else None   # step 2 comes unannounced
+            loss_g = graphed(batches[bi], nxt)
+            loss_e = training.train_step(nets[1], loss_fn, batches[bi])
+            assert abs(float(loss_g) - float(loss_e)) <= 1e-4 * abs(float(loss_e)) + 1e-6, (step, float(loss_g), float(loss_e))
+            for (na, pa), (nb, pb) in zip(nets[0].named_parameters(), nets[1].named_parameters()):
+                scale = float(pb.grad.abs().max()) + 1e-12
+                assert float((pa.grad - pb.grad).abs().max()) <= 2e-3 * scale, (step, na)
+        for (na, ba), (nb, bb) in zip(nets[0].named_buffers(), nets[1].named_buffers()):
+            torch.testing.assert_close(ba.float(), bb.float(), rtol=1e-4, atol=1e-5, msg=na)
+    finally:
+        torch.backends.cudnn.allow_tf32 = old
