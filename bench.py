@@ -538,7 +538,7 @@ def main():
     # inputs: 16 scenes per rank, resident in HBM in ROT rotated variants so that a step's
     # input was last touched ROT-1 steps (and >> 126 MB of other traffic) ago
     ROT = 8 if args.workload == "backbone" else 4     # a 132-d batch is 346 MB: larger than L2 on its own
-    if args.in_flight > ROT and args.workload == "backbone":
+    if args.in_flight > ROT:
         ROT = args.in_flight                          # one resident input (and graph) per forward in flight
     host_batch = synthetic.make_batch(BATCH, NUM_POINTS, features, first_scene=rank * BATCH)
     host_pinned = [torch.roll(host_batch, shifts=997 * i, dims=1).contiguous().pin_memory() for i in range(ROT)]
