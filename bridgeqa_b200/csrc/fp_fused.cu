@@ -189,17 +189,34 @@ fp_mlp_kernel(const FpParams P) {
       // Ascending k inside this thread's range, so "strictly smaller than the current j-th best" is the
       // reference's cascade; the insert is branch-free, and skipped for the whole warp when no lane's
       // third-best improves (the common case after the first few dozen points).
-#pragma unroll 4
-      for (int t = t0; t < t1; ++t) {
+      // Four points per step: their distances are independent (the loop is bound by instruction latency,
+      // two warps per scheduler), ONE vote decides whether any lane improves on any of the four, and the
+      // inserts -- no-ops for a point that does not improve -- run in ascending order.
+      auto insert = [&](float d, int k) {
+        const bool l1 = d < best1, l2 = d < best2, l3 = d < best3;
+        best3 = l2 ? best2 : (l3 ? d : best3); i3 = l2 ? i2 : (l3 ? k : i3);
+        best2 = l1 ? best1 : (l2 ? d : best2); i2 = l1 ? i1 : (l2 ? k : i2);
+        best1 = l1 ? d : best1;                i1 = l1 ? k : i1;
+      };
+      int t = t0;
+      for (; t + 4 <= t1; t += 4) {
+        float d[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float4 kq = s_known4[t + e];
+          d[e] = sqdist3(ux, uy, uz, kq.x, kq.y, kq.z);
+        }
+        const float dm = fminf(fminf(d[0], d[1]), fminf(d[2], d[3]));
+        // (a NaN distance never improves anything: d < best is false, and fminf drops it here)
+        if (__any_sync(0xffffffffu, dm < best3)) {
+#pragma unroll
+          for (int e = 0; e < 4; ++e) insert(d[e], base + t + e);
+        }
+      }
+      for (; t < t1; ++t) {
         const float4 kq = s_known4[t];
         const float d = sqdist3(ux, uy, uz, kq.x, kq.y, kq.z);
-        if (__any_sync(0xffffffffu, d < best3)) {
-          const int k = base + t;
-          const bool l1 = d < best1, l2 = d < best2, l3 = d < best3;
-          best3 = l2 ? best2 : (l3 ? d : best3); i3 = l2 ? i2 : (l3 ? k : i3);
-          best2 = l1 ? best1 : (l2 ? d : best2); i2 = l1 ? i1 : (l2 ? k : i2);
-          best1 = l1 ? d : best1;                i1 = l1 ? k : i1;
-        }
+        if (__any_sync(0xffffffffu, d < best3)) insert(d, base + t);
       }
     }
     if (half == 1) {
