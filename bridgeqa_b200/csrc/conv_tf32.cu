@@ -156,8 +156,6 @@ struct ConvParams {
   float *y;                      // (b, cout, p)
   const float *shift;            // per-channel shift of the statistics (or NULL: 0)
   double *sums;                  // [2 * cout]: sum (y - shift), sum (y - shift)^2; or NULL
-  float *dbg;                    // developer builds: first stage of the first tile is dumped here
-  int flags;                     // measurement only (BQA_CONV_FLAGS): 1 = no stores, 2 = no statistics
 };
 
 __global__ void __launch_bounds__(kThreads, 1)
@@ -231,11 +229,6 @@ conv1x1_tf32_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_const
           const uint32_t s = g % nst, u = g / nst;
           wait_bar(smem_u32(&bars.full[s]), u & 1, 3);
           umma::fence_after_sync();
-          if (P.dbg && g == 0 && blockIdx.x == 0 && blockIdx.y == 0) {
-            const float *wsp = reinterpret_cast<const float *>(smem + s * stage_bytes);
-            for (int i = 0; i < 1024; ++i) P.dbg[i] = wsp[i];
-            for (int i = 0; i < 1024; ++i) P.dbg[1024 + i] = wsp[w_bytes / 4 + i];
-          }
           // descriptors of this stage = stage-0 descriptors + (s * stage_bytes) >> 4 in the address field
           const uint64_t ad_s = ad0 + (uint64_t)(s * (stage_bytes >> 4));
           const uint64_t bd_s = bd0 + (uint64_t)(s * (stage_bytes >> 4));
@@ -285,7 +278,7 @@ conv1x1_tf32_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_const
           umma::wait_ld();
           // y: this warp's 32 channels x 32 positions go through a swizzled staging tile (row = channel,
           // 128 B) and one TMA store, which also clips channels >= cout and positions >= p
-          if (!(P.flags & 1)) {
+          {
             if (lane == 0) bulk_wait_read<1>();                 // the store that last read this buffer is done
             __syncwarp();
             const uint32_t tile_s = stage_out + (uint32_t)buf * 4096u;
@@ -303,7 +296,7 @@ conv1x1_tf32_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_const
             }
             buf ^= 1;
           }
-          if (co < P.cout && !(P.flags & 2)) {
+          if (co < P.cout) {
             if (p0 + c0 + 32 <= P.p) {
               // four independent chains per sum (a 32-long dependent chain would cost ~130 cycles)
               float a1[4] = {0.f, 0.f, 0.f, 0.f}, a2[4] = {0.f, 0.f, 0.f, 0.f};
@@ -492,14 +485,6 @@ int conv1x1_tf32_forward(int b, int cin, int cout, int p, const float *x, const 
   P.tiles_per_scene = ceil_div(p, kTileN);
   P.num_tiles = b * P.tiles_per_scene;
   P.y = y; P.shift = shift; P.sums = sums;
-  P.dbg = nullptr;
-  static const int flags = [] { const char *e = getenv("BQA_CONV_FLAGS"); return e ? atoi(e) : 0; }();
-  P.flags = flags;
-  if (const char *e = getenv("BQA_CONV_DEBUG")) {
-    static float *dbg = nullptr;
-    if (!dbg) cudaMalloc(&dbg, 2048 * sizeof(float));
-    if (atoi(e)) P.dbg = dbg;
-  }
   CUtensorMap tm_x, tm_w;
   if (int rc = make_map(&tm_x, x, p, cin, b, p, (long long)cin * p, 32, kKC, true)) return rc;
   if (int rc = make_map(&tm_w, w, cin, cout, 1, ldw, (long long)cout * ldw, kKC, P.rows)) return rc;
@@ -513,14 +498,6 @@ int conv1x1_tf32_forward(int b, int cin, int cout, int p, const float *x, const 
   const int slabs = ceil_div(cout, 256);
   dim3 grid((unsigned)min(P.num_tiles, max(1, sm_count() / slabs)), (unsigned)slabs);
   conv1x1_tf32_kernel<<<grid, kThreads, smem, stream>>>(tm_x, tm_w, tm_y, P);
-  if (P.dbg) {
-    static float host[2048];
-    cudaMemcpy(host, P.dbg, sizeof(host), cudaMemcpyDeviceToHost);
-    fprintf(stderr, "[bqa conv dbg] W stage, rows 0-3 (32 floats each):\n");
-    for (int r = 0; r < 4; ++r) { for (int i = 0; i < 32; ++i) fprintf(stderr, "%g ", host[r * 32 + i]); fprintf(stderr, "\n"); }
-    fprintf(stderr, "[bqa conv dbg] X stage, rows 0-3 of block 0:\n");
-    for (int r = 0; r < 4; ++r) { for (int i = 0; i < 32; ++i) fprintf(stderr, "%g ", host[1024 + r * 32 + i]); fprintf(stderr, "\n"); }
-  }
   count_launch();
   return check_launch("conv1x1_tf32_kernel");
 }

@@ -387,7 +387,7 @@ int launch_stream(int b, int n, int m, const float4 *sorted, const float *xyz, i
 int stream_ppl(int n) {
   // shortest runs whose count fits one owner thread each and whose min-distances fit shared memory
   static const int forced = [] { const char *e = getenv("BQA_FPS_STREAM_PPL"); return e ? atoi(e) : 0; }();
-  for (int ppl = 1; ppl <= 4; ppl *= 2) {
+  for (int ppl = 1; ppl <= 2; ppl *= 2) {
     if (forced && ppl != forced) continue;
     const int nr = ceil_div(n, 32 * ppl);
     if (nr <= 1024 && (size_t)nr * 32 * ppl * sizeof(float) <= kStreamSmemMax) return ppl;
@@ -407,7 +407,6 @@ int fps_stream_dispatch(int b, int n, int m, const float *xyz, const void *grid,
   switch (stream_ppl(n)) {
     case 1: return launch_stream<1>(b, n, m, sorted, xyz, idxs, new_xyz, stream);
     case 2: return launch_stream<2>(b, n, m, sorted, xyz, idxs, new_xyz, stream);
-    case 4: return launch_stream<4>(b, n, m, sorted, xyz, idxs, new_xyz, stream);
   }
   return set_error(BQA_ERR_UNSUPPORTED, "fps (stream): n=%d not supported", n);
 }

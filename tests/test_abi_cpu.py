@@ -81,6 +81,9 @@ def test_sass_histogram_in_profiles_matches_the_built_library():
     assert some("sa_v2_kernel", "UTCHMMA") and some("sa_v2_kernel", "LDTM") and some("sa_v2_kernel", "LDGSTS")
     assert some("fp_mlp_kernel", "UTCHMMA") and some("fp_mlp_kernel", "LDTM") and some("fp_mlp_kernel", "UBLKCP")
     assert some("fps_sorted_kernel", "STAS") and some("fps_stream_kernel", "CREDUX")
+    # training convolutions: TMA tensor-map loads and stores around kind::tf32 MMAs
+    assert some("conv1x1_tf32_kernel", "UTMALDG") and some("conv1x1_tf32_kernel", "UTMASTG")
+    assert some("conv1x1_tf32_kernel", "UTCHMMA") and some("wgrad_tf32_kernel", "UTMALDG") and some("wgrad_tf32_kernel", "UTCHMMA")
     committed = json.load(open(os.path.join(ROOT, "profiles", "r2_sass_histogram.json")))
     assert committed["arch"] == ["sm_100a"] and committed["totals"]["UTCHMMA"] > 0 and committed["totals"]["LDTM"] > 0
 
