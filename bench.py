@@ -266,7 +266,7 @@ def sms_occupied(name, dims, sms=148):
     SM-time budget of the in-flight regime, where the step is bound by total SM-time, not by latency."""
     if name == "bqa_furthest_point_sampling_grid_lean":
         b, n = dims[:2]
-        if 512 <= n <= 57000:          # one-SM kernel (fps_stream.cu): one CTA per scene
+        if 512 <= n <= 53440:          # one-SM kernel (fps_stream.cu): one CTA per scene
             return min(sms, b)
         return min(sms, b * -(-n // (768 * 18)))
     if name == "bqa_furthest_point_sampling_grid":

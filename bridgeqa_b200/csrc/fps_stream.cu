@@ -398,7 +398,7 @@ int stream_ppl(int n) {
 }  // namespace
 
 // scenes the one-SM kernel takes: the tie key assumes the reference's block size 512 (n >= 512), and
-// the running min-distances of the scene must fit one SM's shared memory (n <= ~57k)
+// the running min-distances of the scene must fit one SM's shared memory (n <= ~53k)
 bool fps_stream_supported(int n, int m) { return n >= 512 && m >= 1 && stream_ppl(n) != 0; }
 
 int fps_stream_dispatch(int b, int n, int m, const float *xyz, const void *grid, int *idxs,

@@ -118,6 +118,9 @@ FPS_GRID_CASES = [
     (2, 12345, 300, 0.05), (2, 20000, 512, 0.2), (4, 40000, 700, 0.2), (1, 40000, 2048, 3.0),
     (1, 70000, 96, 0.2), (1, 100000, 64, 0.2), (1, 147456, 40, 0.2),
     (1, 60000, 64, 0.2), (1, 90000, 48, 0.2),      # throughput variant: clusters of 5 and 7 CTAs
+    # one-SM throughput kernel (fps_stream.cu): 32-point runs up to 32768 points, 64-point runs up to
+    # 53440 (its min-distances fill shared memory), the cluster variant beyond
+    (1, 32768, 100, 0.2), (1, 32769, 100, 0.2), (1, 53440, 64, 0.2), (1, 53441, 64, 0.2),
 ]
 
 
