@@ -36,7 +36,11 @@
 //    entry, so the ~21 active runs are processed by 21 warps; second CTA barrier, records through shared
 //    memory): bit-exact, 1.30 us with 20 warps, 1.54 us with 32 -- the busiest warp's 2-3 runs are not
 //    what bounds an iteration: with ~4500 warp-instructions per iteration the SM's four schedulers are
-//    ~50 % busy (ncu) and the rest is the dependent chain fold -> box test -> L2 load -> reduce -> post.
+//    ~50 % busy (ncu) and the rest is the dependent chain fold -> box test -> L2 load -> reduce -> post;
+//  * TWO scenes per CTA (min-distances in global memory too -- the grid's spent cell_of words --, 16 warps
+//    and a named barrier per scene, so two chains share the schedulers): bit-exact; with 128-point runs
+//    2.21 us per iteration for both scenes = 36 SM-ms per batch instead of 40 at 1.8x the latency of a
+//    call; with 64-point runs and two owner slots per lane 2.66 us = 43 SM-ms.  Not worth the latency.
 #include <cstdio>
 #include <cstdlib>
 
