@@ -62,6 +62,9 @@ class OverlappedGradReducer(object):
         self.group = group
         self.world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
         params = [p for p in module.parameters() if p.requires_grad]
+        if any(p.dtype != torch.float32 for p in params):
+            raise RuntimeError("OverlappedGradReducer: fp32 parameters only (the buckets are flat fp32 buffers "
+                               "that the gradients are views of)")
         self.params = list(reversed(params))
         total = sum(p.numel() for p in self.params)
         target = max(1, -(-total // max(1, int(nbuckets))))
