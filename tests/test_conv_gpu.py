@@ -225,3 +225,54 @@ def test_graphed_train_step_equals_eager_steps():
             torch.testing.assert_close(ba.float(), bb.float(), rtol=1e-4, atol=1e-5, msg=na)
     finally:
         torch.backends.cudnn.allow_tf32 = old
+
+
+def test_train_step_at_the_benchmarked_size_graphed_vs_eager_vs_cudnn():
+    """configs[3] as bench.py times it: VoteNetDetector, C = 132, 16 scenes x 40000 points, train-mode BN,
+    torch's default TF32 switch.  (a) The step replayed from the two alternating CUDA graphs gives the eager
+    step's loss (1e-4) for two consecutive, announced batches; (b) the eager step runs every SharedMLP block
+    on the tcgen05 kernels (call counts); (c) its backbone output agrees with the same step on cuDNN's TF32
+    convolutions to 3e-2 of the tensor's max (ten TF32 layers deep, through BatchNorm)."""
+    from bridgeqa_b200 import detector, profiler, synthetic, training
+    old = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = True
+    try:
+        feats, bsz = 132, 16
+        batches = [synthetic.make_batch(bsz, 40000, feats, first_scene=300 + bsz * i).cuda() for i in range(2)]
+        loss_fn = training.ProjectionLoss().cuda()
+
+        def fresh():
+            torch.manual_seed(0)
+            return synthetic.fill_state_dict(detector.VoteNetDetector(feats), seed=0).cuda()
+        # eager, tcgen05 convs
+        net_e = fresh()
+        net_e.train()
+        with profiler.KernelTimer() as kt:
+            out = net_e({"point_clouds": batches[0]})
+            loss_e0 = loss_fn(out)
+            loss_e0.backward()
+        names = [r[0] for r in kt.records]
+        assert names.count("bqa_conv1x1_tf32_wgrad") == 19 and names.count("bqa_conv1x1_tf32_forward") == 37
+        feat_e = out["fp2_features"].detach().clone()
+        loss_e1 = training.train_step(net_e, loss_fn, batches[1])
+        # graphed
+        net_g = fresh()
+        graphed = training.GraphedTrainStep(net_g, loss_fn, batches[0])
+        loss_g0 = graphed(batches[0], batches[1])
+        loss_g1 = graphed(batches[1], None)
+        for a, b_ in ((loss_g0, loss_e0), (loss_g1, loss_e1)):
+            assert abs(float(a) - float(b_)) <= 1e-4 * abs(float(b_)) + 1e-7, (float(a), float(b_))
+        del graphed, net_g
+        # cuDNN TF32 convs
+        net_c = fresh()
+        net_c.train()
+        train_fused.set_conv_enabled(False)
+        try:
+            out_c = net_c({"point_clouds": batches[0]})
+        finally:
+            train_fused.set_conv_enabled(True)
+        err = float((feat_e - out_c["fp2_features"]).abs().max() / out_c["fp2_features"].abs().max())
+        assert err < 3e-2, "fp2_features vs cuDNN TF32: %g of the tensor's max" % err
+    finally:
+        torch.backends.cudnn.allow_tf32 = old
+        torch.cuda.empty_cache()
