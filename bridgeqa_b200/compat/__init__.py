@@ -14,7 +14,9 @@ sys.modules BEFORE the reference modules are imported:
                      reference also uses) resolve to bridgeqa_b200's mirrors, so
                      models/backbone_module.py, voting_module.py and proposal_module.py pick up
                      the fused tcgen05 SA kernels in eval mode.  state_dict keys are identical,
-                     so checkpoints load either way.
+                     so checkpoints load either way.  `utils.nn_distance` (lib/loss_helper.py:13)
+                     resolves to the one-kernel version as well: the reference's own VoteNet losses
+                     then run unchanged on it (bit-identical distances, same gradients).
 """
 import sys
 import types
@@ -45,6 +47,10 @@ def install(level="modules"):
     sub = _real_or_synthetic_package("lib.pointnet2", lib)
     sub.pointnet2_utils, sub.pointnet2_modules, sub.pytorch_utils = (
         pointnet2_utils, pointnet2_modules, pytorch_utils)
+    from .. import nn_distance
+    utils = _real_or_synthetic_package("utils", None)
+    utils.nn_distance = nn_distance
+    sys.modules["utils.nn_distance"] = nn_distance
 
 
 def _find_package_dir(name):
@@ -53,7 +59,7 @@ def _find_package_dir(name):
     rel = os.path.join(*name.split("."))
     for base in list(sys.path) + [os.getcwd()]:
         d = os.path.join(base or os.getcwd(), rel)
-        if os.path.isdir(d) and (os.path.exists(os.path.join(d, "__init__.py")) or name == "lib"):
+        if os.path.isdir(d) and (os.path.exists(os.path.join(d, "__init__.py")) or name in ("lib", "utils")):
             return d
     return None
 

@@ -50,7 +50,8 @@ def available():
 REF_ROOT = "/root/reference"
 TREE_DIR = os.path.join(HERE, "_ref", "ref_tree")
 STAGED = ("lib/pointnet2/pointnet2_modules.py", "lib/pointnet2/pointnet2_utils.py",
-          "lib/pointnet2/pytorch_utils.py", "models/backbone_module.py", "models/voting_module.py")
+          "lib/pointnet2/pytorch_utils.py", "models/backbone_module.py", "models/voting_module.py",
+          "lib/loss_helper.py", "utils/nn_distance.py")
 
 
 def stage_python_layer():

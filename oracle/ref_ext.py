@@ -62,3 +62,38 @@ def load_reference_modules(ext_module):
     finally:
         os.chdir(cwd)
     return backbone_module, voting_module, utils
+
+
+def load_reference_loss_helper():
+    """The UNMODIFIED lib/loss_helper.py (+ utils/nn_distance.py) of the reference, staged by
+    build_ref.stage_python_layer(), or None.  Its other imports (lib.ap_helper, lib.loss, utils.box_util,
+    icecream) are only used by the QA / evaluation functions of that file and are satisfied with empty
+    stand-ins; the three detection losses run as written."""
+    import types
+    tree = os.path.join(HERE, "_ref", "ref_tree")
+    if not os.path.exists(os.path.join(tree, "lib", "loss_helper.py")):
+        return None
+
+    def stub(name, **attrs):
+        m = types.ModuleType(name)
+        m.__dict__.update(attrs)
+        sys.modules[name] = m
+        return m
+    for stale in ("lib", "lib.loss_helper", "utils", "utils.nn_distance"):
+        sys.modules.pop(stale, None)
+    stub("icecream", ic=lambda *a, **k: None)
+    lib = stub("lib")
+    lib.__path__ = [os.path.join(tree, "lib")]
+    stub("lib.ap_helper", parse_predictions=None)
+    stub("lib.loss", SoftmaxRankingLoss=None)
+    utils = stub("utils")
+    utils.__path__ = [os.path.join(tree, "utils")]
+    stub("utils.box_util", get_3d_box=None, get_3d_box_batch=None, box3d_iou=None, box3d_iou_batch=None)
+    cwd = os.getcwd()
+    sys.path.insert(0, tree)
+    os.chdir(tree)
+    try:
+        return importlib.import_module("lib.loss_helper")
+    finally:
+        os.chdir(cwd)
+        sys.path.remove(tree)

@@ -35,6 +35,10 @@ assert all(net.state_dict()[k].shape == mine.state_dict()[k].shape for k in mine
 mine.load_state_dict(net.state_dict(), strict=True)
 import pointnet2._ext as e
 assert e.furthest_point_sampling.__module__ == "bridgeqa_b200.ext"
+if %(level)r == "modules":
+    import utils.nn_distance as nnd, utils.box_util        # the override and a real sibling of it
+    assert nnd.__name__ == "bridgeqa_b200.nn_distance" and hasattr(nnd, "huber_loss")
+    assert os.path.samefile(os.path.dirname(utils.box_util.__file__), os.path.join(%(ref)r, "utils"))
 mod = sys.modules[type(net.sa1).__module__]
 print("OK", type(net.sa1).__module__, getattr(mod, "__file__", ""))
 try:
