@@ -860,6 +860,12 @@ def main():
                 ref = json.loads(rr.stdout.strip().splitlines()[-1])
                 if "value" in ref:
                     ref["speedup_device_resident"] = round(value / ref["value"], 2)
+                if "checksum_fp2_features" in ref:
+                    # same weights (seed 0), same batch (scenes 0-15): mean |fp2_features| of this repo's forward
+                    with torch.no_grad():
+                        mine = float(net({"point_clouds": dev_inputs[0]})["fp2_features"].double().abs().mean())
+                    ref["checksum_fp2_features_this_repo"] = mine
+                    ref["checksum_rel_diff"] = abs(mine - ref["checksum_fp2_features"]) / abs(ref["checksum_fp2_features"])
                 line["ref_ext"] = ref
             except Exception as e:
                 line["ref_ext"] = {"unavailable": repr(e)[:200]}
