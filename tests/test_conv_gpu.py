@@ -276,3 +276,35 @@ def test_train_step_at_the_benchmarked_size_graphed_vs_eager_vs_cudnn():
     finally:
         torch.backends.cudnn.allow_tf32 = old
         torch.cuda.empty_cache()
+
+
+def test_graphed_train_step_recaptures_when_bn_momentum_changes():
+    """BNMomentumScheduler (lib/solver.py:271-279, pytorch_utils.py:299-333) rewrites every BatchNorm's momentum
+    per epoch; the value is baked into the captured graphs, so GraphedTrainStep must notice and re-capture:
+    running statistics after the change follow the NEW momentum exactly like the eager step's."""
+    from bridgeqa_b200 import detector, synthetic, training
+    from bridgeqa_b200 import pytorch_utils as pu
+    old = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = True
+    try:
+        nets = []
+        for _ in range(2):
+            torch.manual_seed(0)
+            nets.append(synthetic.fill_state_dict(detector.Pointnet2Backbone(input_feature_dim=7), seed=6).cuda())
+        loss_fn = lambda out: out["fp2_features"].pow(2).mean()
+        pc = synthetic.make_batch(2, 5000, 7, first_scene=77).cuda()
+        graphed = training.GraphedTrainStep(nets[0], loss_fn, pc)
+        scheds = [pu.BNMomentumScheduler(n, bn_lambda=lambda e: 0.5 * 0.5 ** e) for n in nets]
+        for epoch in range(2):
+            for s in scheds:
+                s.step(epoch)
+            graphed(pc, pc)
+            training.train_step(nets[1], loss_fn, pc)
+        rm_g = nets[0].sa1.mlp_module.layer0.bn.bn.running_mean
+        rm_e = nets[1].sa1.mlp_module.layer0.bn.bn.running_mean
+        assert float(nets[0].sa1.mlp_module.layer0.bn.bn.momentum) == 0.25
+        torch.testing.assert_close(rm_g, rm_e, rtol=1e-4, atol=1e-5)
+        nb = nets[0].sa1.mlp_module.layer0.bn.bn.num_batches_tracked
+        assert int(nb) == int(nets[1].sa1.mlp_module.layer0.bn.bn.num_batches_tracked)
+    finally:
+        torch.backends.cudnn.allow_tf32 = old
