@@ -50,6 +50,19 @@ __device__ __forceinline__ uint32_t pack16_relu(float lo, float hi, int fp16) {
   return d;
 }
 
+// 8 consecutive floats of a feature row: one 256-bit load (LDG.E.256, sm_100) when the row is 32-byte aligned
+__device__ __forceinline__ void ldg_row32(const float *p, float (&v)[8], int wide) {
+  if (wide) {
+    asm("ld.global.nc.v8.f32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+        : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7])
+        : "l"(p));
+  } else {
+    const float4 a = __ldg(reinterpret_cast<const float4 *>(p));
+    const float4 b = __ldg(reinterpret_cast<const float4 *>(p + 4));
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+  }
+}
+
 __device__ __forceinline__ void bulk_load(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar) {
   asm volatile(
       "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
@@ -68,7 +81,11 @@ struct FpParams {
   const float *b1, *b2;
   float *out_cm, *out_pm;
   int fp16;
+  int wide;                               // known_feat rows are 32-byte aligned: one 256-bit load per lane
   int num_tiles, tiles_per_scene;
+#ifdef BQA_SA_TRACE
+  int dbg;
+#endif
 };
 
 #ifdef BQA_SA_TRACE
@@ -78,7 +95,10 @@ __device__ long long g_fp_trace[64];
 #define FP_TRACE(i)
 #endif
 
-constexpr int kThreads = 256;      // 8 warps: two threads per row (warp w and w + 4 share TMEM lane quarter w % 4)
+constexpr int kThreads = 512;      // 16 warps: four threads per row (warps w, w + 4, w + 8, w + 12 share TMEM lane quarter w % 4)
+constexpr int kParts = kThreads / kRows;        // threads per row: each scans 1 / kParts of the known points and
+                                                // converts 1 / kParts of the epilogue columns
+constexpr int kRowsPerWarp = kRows / (kThreads / 32);   // rows a warp gathers (8)
 
 struct NnRow { int i1, i2, i3; float w1, w2, w3; };
 
@@ -97,7 +117,10 @@ fp_mlp_kernel(const FpParams P) {
   constexpr int kAVecs = kChunk / 8 * kRows;          // 1024 x 16 B = 16 KB per stage
   constexpr int kWVecs = kChunk / 8 * kWidth;         // 2048 x 16 B = 32 KB per stage
   constexpr int kXVecs = kWidth / 8 * kRows;          // 4096 x 16 B = 64 KB
-  extern __shared__ __align__(128) unsigned char smem_raw[];
+  extern __shared__ __align__(1024) unsigned char smem_unaligned[];
+  // 1024-byte alignment: the A stages hold 128-byte swizzle atoms
+  // (pointer arithmetic on the array, not an integer round trip: the accesses stay LDS / STS)
+  unsigned char *smem_raw = smem_unaligned + ((1024u - (smem_u32(smem_unaligned) & 1023u)) & 1023u);
   uint4 *a_st = reinterpret_cast<uint4 *>(smem_raw);                  // [2][kAVecs]
   uint4 *w_st = a_st + 2 * kAVecs;                                    // [2][kWVecs]
   uint4 *x1 = w_st + 2 * kWVecs;                                      // [kXVecs]
@@ -105,15 +128,15 @@ fp_mlp_kernel(const FpParams P) {
   float *s_b1 = s_known + kKnownTile * 4;
   float *s_b2 = s_b1 + kWidth;
   NnRow *s_nn = reinterpret_cast<NnRow *>(s_b2 + kWidth);             // [kRows]: neighbours + weights of every row
-  float *s_merge = reinterpret_cast<float *>(s_nn + kRows);           // [kRows][6]: second half's candidates
-  uint64_t *s_bar = reinterpret_cast<uint64_t *>(s_merge + kRows * 6);  // wfull[2], mdone[2]
+  float *s_merge = reinterpret_cast<float *>(s_nn + kRows);           // [kParts - 1][kRows][6]: the other parts' candidates
+  uint64_t *s_bar = reinterpret_cast<uint64_t *>(s_merge + (kParts - 1) * kRows * 6);  // wfull[2], mdone[2]
   uint32_t *s_tmem = reinterpret_cast<uint32_t *>(s_bar + 4);
 
   const int tid = threadIdx.x;
   const int warp = tid >> 5, lane = tid & 31;
   const int quarter = warp & 3;            // TMEM lane quarter of this warp
-  const int half = warp >> 2;              // 0 / 1: which half of the known set / of the columns this thread takes
-  const int row = quarter * 32 + lane;     // row of the tile this thread shares with thread (row, half ^ 1)
+  const int half = warp >> 2;              // 0 .. kParts-1: which part of the known set / of the columns this thread takes
+  const int row = quarter * 32 + lane;     // row of the tile this thread shares with kParts - 1 others
   for (int i = tid; i < kWidth; i += kThreads) { s_b1[i] = P.b1[i]; s_b2[i] = P.b2[i]; }
   const uint32_t wfull0 = smem_u32(&s_bar[0]), mdone0 = smem_u32(&s_bar[2]);
   if (tid == 0) {
@@ -154,13 +177,16 @@ fp_mlp_kernel(const FpParams P) {
     // layer-1 MMA has read them
     const bool skip_early = P.skip16 != nullptr && P.c_skip * kRows * 2 <= kXVecs * 16;
     if (skip_early) {
-      const int g4e = lane >> 3;
+      // a quarter warp copies 128 contiguous bytes (64 channels) of one row into the 128-byte-swizzled layout:
+      // K block kb = 64 channels = 16 KB [128 rows][128 B], chunk ^ (row & 7)
+      const int rqe = lane >> 3, q8e = lane & 7;
 #pragma unroll 1
-      for (int it = 0; it < 2; ++it) {
-        const int r = warp * 16 + it * 8 + (lane & 7);
+      for (int it = 0; it < kRowsPerWarp / 4; ++it) {
+        const int r = warp * kRowsPerWarp + it * 4 + rqe;
         const int jr = min(row0 + r, P.n - 1);
-        const uint16_t *src = P.skip16 + ((size_t)scene * P.n + jr) * P.skip16_stride;
-        for (int q = g4e; q < P.c_skip / 8; q += 4) cp_async16(smem_u32(x1 + q * kRows + r), src + q * 8);
+        const uint16_t *src = P.skip16 + ((size_t)scene * P.n + jr) * P.skip16_stride + q8e * 8;
+        const uint32_t d = x_addr + (uint32_t)(r * 128 + ((q8e ^ (r & 7)) << 4));
+        for (int kb = 0; kb < P.c_skip / kChunk; ++kb) cp_async16(d + kb * (kRows * 128), src + kb * kChunk);
       }
     }
     FP_TRACE(0)
@@ -184,8 +210,8 @@ fp_mlp_kernel(const FpParams P) {
         s_known4[t] = make_float4(kp[0], kp[1], kp[2], 0.f);
       }
       __syncthreads();
-      const int hn = (tn + 1) / 2;
-      const int t0 = half * hn, t1 = min(tn, t0 + hn);
+      const int hn = (tn + kParts - 1) / kParts;
+      const int t0 = min(tn, half * hn), t1 = min(tn, t0 + hn);
       // Ascending k inside this thread's range, so "strictly smaller than the current j-th best" is the
       // reference's cascade; the insert is branch-free, and skipped for the whole warp when no lane's
       // third-best improves (the common case after the first few dozen points).
@@ -219,28 +245,35 @@ fp_mlp_kernel(const FpParams P) {
         if (__any_sync(0xffffffffu, d < best3)) insert(d, base + t);
       }
     }
-    if (half == 1) {
-      float *mg = s_merge + row * 6;
+    if (half >= 1) {
+      float *mg = s_merge + ((half - 1) * kRows + row) * 6;
       mg[0] = best1; mg[1] = best2; mg[2] = best3;
       mg[3] = __int_as_float(i1); mg[4] = __int_as_float(i2); mg[5] = __int_as_float(i3);
     }
     __syncthreads();
     if (half == 0) {
-      const float *mg = s_merge + row * 6;
-      float ad[3] = {best1, best2, best3}, bd[3] = {mg[0], mg[1], mg[2]};
-      int ai[3] = {i1, i2, i3}, bi[3] = {__float_as_int(mg[3]), __float_as_int(mg[4]), __float_as_int(mg[5])};
-      float od[3]; int oi[3];
-      int pa = 0, pb = 0;
+      // merge the parts' sorted triples one after the other: each is the three smallest (distance, index)
+      // pairs of its range, so the three smallest of the union are the reference's result
+      float od[3] = {best1, best2, best3};
+      int oi[3] = {i1, i2, i3};
 #pragma unroll
-      for (int t = 0; t < 3; ++t) {
-        // entries never filled keep (inf, 0) on both sides: either choice writes (inf, 0) like the reference
-        const float da = pa == 0 ? ad[0] : pa == 1 ? ad[1] : ad[2];
-        const float db = pb == 0 ? bd[0] : pb == 1 ? bd[1] : bd[2];
-        const int ia = pa == 0 ? ai[0] : pa == 1 ? ai[1] : ai[2];
-        const int ib = pb == 0 ? bi[0] : pb == 1 ? bi[1] : bi[2];
-        const bool take_b = nn_less(db, ib, da, ia);
-        od[t] = take_b ? db : da; oi[t] = take_b ? ib : ia;
-        if (take_b) ++pb; else ++pa;
+      for (int part = 1; part < kParts; ++part) {
+        const float *mg = s_merge + ((part - 1) * kRows + row) * 6;
+        const float ad[3] = {od[0], od[1], od[2]}, bd[3] = {mg[0], mg[1], mg[2]};
+        const int ai[3] = {oi[0], oi[1], oi[2]};
+        const int bi[3] = {__float_as_int(mg[3]), __float_as_int(mg[4]), __float_as_int(mg[5])};
+        int pa = 0, pb = 0;
+#pragma unroll
+        for (int t = 0; t < 3; ++t) {
+          // entries never filled keep (inf, 0) on both sides: either choice writes (inf, 0) like the reference
+          const float da = pa == 0 ? ad[0] : pa == 1 ? ad[1] : ad[2];
+          const float db = pb == 0 ? bd[0] : pb == 1 ? bd[1] : bd[2];
+          const int ia = pa == 0 ? ai[0] : pa == 1 ? ai[1] : ai[2];
+          const int ib = pb == 0 ? bi[0] : pb == 1 ? bi[1] : bi[2];
+          const bool take_b = nn_less(db, ib, da, ia);
+          od[t] = take_b ? db : da; oi[t] = take_b ? ib : ia;
+          if (take_b) ++pb; else ++pa;
+        }
       }
       const float r1 = __fdiv_rn(1.0f, __fadd_rn(__fsqrt_rn(od[0]), 1e-8f));
       const float r2 = __fdiv_rn(1.0f, __fadd_rn(__fsqrt_rn(od[1]), 1e-8f));
@@ -254,10 +287,9 @@ fp_mlp_kernel(const FpParams P) {
     __syncthreads();
 
     FP_TRACE(1)
-    // ---- gather geometry: a warp serves 16 rows of the tile, 8 at a time; lane = (row r8, chunk group g):
-    // the four lanes of a row read 4 x 32 contiguous bytes of each source row (full 128-byte lines) and
-    // a quarter warp writes 8 consecutive rows of one 16-byte chunk column (conflict-free)
-    const int g4 = lane >> 3;
+    // ---- gather geometry: a warp serves 8 rows of the tile
+    const int g4 = lane >> 3;                  // skip channels (canonical layout): lane = (row lane & 7, chunk group g4)
+    const int rq = lane >> 3, q8 = lane & 7;   // interpolated channels: lane = (row of a quad, 16-byte chunk)
     for (int c = 0; c < nchunks; ++c) {
       const uint32_t g = gchunk + c, s = g & 1;
       // stage s^1 is free once the MMAs of slice g-1 are done: prefetch the next weights
@@ -273,43 +305,41 @@ fp_mlp_kernel(const FpParams P) {
         // ---- layer-1 A operand, channels [c*64, c*64+64) of all 128 rows ---------------------
         uint4 *dst = a_st + s * kAVecs;
         const int k0 = c * kChunk;
+        if (k0 < P.c_known) {
+          // interpolated channels: a quarter warp takes one row and reads 256 contiguous bytes (two full
+          // lines) of each of its three neighbour rows, 32 bytes per lane; the warp's 8 rows are two such
+          // passes, all 6 loads of a lane in flight before the first use.  The 16-byte results go to the
+          // 128-byte-swizzled K-major layout (row pitch 128 B, chunk ^ (row & 7)), which the 8 lanes of a
+          // row write without bank conflicts.
+          constexpr int kPasses = kRowsPerWarp / 4;
+          float pv[kPasses][3][8];
+          float wv[kPasses][3];
 #pragma unroll
-        for (int it = 0; it < 2; ++it) {
-          const int r = warp * 16 + it * 8 + (lane & 7);
+          for (int it = 0; it < kPasses; ++it) {
+            const NnRow nr = s_nn[warp * kRowsPerWarp + it * 4 + rq];
+            const float *kf = P.known_feat + (size_t)scene * P.m * P.known_stride + k0 + q8 * 8;
+            ldg_row32(kf + (size_t)nr.i1 * P.known_stride, pv[it][0], P.wide);
+            ldg_row32(kf + (size_t)nr.i2 * P.known_stride, pv[it][1], P.wide);
+            ldg_row32(kf + (size_t)nr.i3 * P.known_stride, pv[it][2], P.wide);
+            wv[it][0] = nr.w1; wv[it][1] = nr.w2; wv[it][2] = nr.w3;
+          }
+#pragma unroll
+          for (int it = 0; it < kPasses; ++it) {
+            const int r = warp * kRowsPerWarp + it * 4 + rq;
+            float v[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e)
+              v[e] = __fmaf_rn(pv[it][2][e], wv[it][2], __fmaf_rn(pv[it][0][e], wv[it][0],
+                                                                 __fmul_rn(pv[it][1][e], wv[it][1])));
+            dst[r * 8 + (q8 ^ (r & 7))] = make_uint4(pack16(v[0], v[1], P.fp16), pack16(v[2], v[3], P.fp16),
+                                                     pack16(v[4], v[5], P.fp16), pack16(v[6], v[7], P.fp16));
+          }
+        } else {
+#pragma unroll
+        for (int it = 0; it < kRowsPerWarp / 8; ++it) {
+          const int r = warp * kRowsPerWarp + it * 8 + (lane & 7);
           const int jr = min(row0 + r, P.n - 1);
-          if (k0 < P.c_known) {
-            const NnRow nr = s_nn[r];
-            const float *f1 = P.known_feat + ((size_t)scene * P.m + nr.i1) * P.known_stride + k0;
-            const float *f2 = P.known_feat + ((size_t)scene * P.m + nr.i2) * P.known_stride + k0;
-            const float *f3 = P.known_feat + ((size_t)scene * P.m + nr.i3) * P.known_stride + k0;
-            // 12 independent 16-byte loads in flight before the first use (the rows are random: the
-            // loop is bound by their latency, not by arithmetic)
-            float4 p1[2][2], p2[2][2], p3[2][2];
-#pragma unroll
-            for (int qq = 0; qq < 2; ++qq) {
-#pragma unroll
-              for (int h = 0; h < 2; ++h) {
-                const int off = (g4 + 4 * qq) * 8 + h * 4;
-                p1[qq][h] = __ldg(reinterpret_cast<const float4 *>(f1 + off));
-                p2[qq][h] = __ldg(reinterpret_cast<const float4 *>(f2 + off));
-                p3[qq][h] = __ldg(reinterpret_cast<const float4 *>(f3 + off));
-              }
-            }
-#pragma unroll
-            for (int qq = 0; qq < 2; ++qq) {
-              const int q = g4 + 4 * qq;
-              float v[8];
-#pragma unroll
-              for (int h = 0; h < 2; ++h) {
-                v[h * 4 + 0] = __fmaf_rn(p3[qq][h].x, nr.w3, __fmaf_rn(p1[qq][h].x, nr.w1, __fmul_rn(p2[qq][h].x, nr.w2)));
-                v[h * 4 + 1] = __fmaf_rn(p3[qq][h].y, nr.w3, __fmaf_rn(p1[qq][h].y, nr.w1, __fmul_rn(p2[qq][h].y, nr.w2)));
-                v[h * 4 + 2] = __fmaf_rn(p3[qq][h].z, nr.w3, __fmaf_rn(p1[qq][h].z, nr.w1, __fmul_rn(p2[qq][h].z, nr.w2)));
-                v[h * 4 + 3] = __fmaf_rn(p3[qq][h].w, nr.w3, __fmaf_rn(p1[qq][h].w, nr.w1, __fmul_rn(p2[qq][h].w, nr.w2)));
-              }
-              dst[q * kRows + r] = make_uint4(pack16(v[0], v[1], P.fp16), pack16(v[2], v[3], P.fp16),
-                                              pack16(v[4], v[5], P.fp16), pack16(v[6], v[7], P.fp16));
-            }
-          } else if (skip_early) {
+          if (skip_early) {
             // already in the X1 buffer
           } else if (P.skip16) {
             // the previous fused layer's 16-bit twin: the very bits this operand needs
@@ -331,6 +361,7 @@ fp_mlp_kernel(const FpParams P) {
             }
           }
         }
+        }
         asm volatile("cp.async.wait_all;" ::: "memory");
       }
       FP_TRACE(2 + 3 * c)
@@ -344,12 +375,16 @@ fp_mlp_kernel(const FpParams P) {
         const bool layer1 = c < nk1;
         const int k0c = c * kChunk;
         const bool early = layer1 && skip_early && k0c >= P.c_known;
-        const uint32_t abase = early ? x_addr + (uint32_t)((k0c - P.c_known) / 8) * kRows * 16
+        const uint32_t abase = early ? x_addr + (uint32_t)((k0c - P.c_known) / kChunk) * (kRows * 128)
                                : layer1 ? a_addr + s * kAVecs * 16
                                         : x_addr + (uint32_t)(c - nk1) * (kChunk / 8) * kRows * 16;
 #pragma unroll
         for (int ks = 0; ks < kChunk / 16; ++ks) {
-          const uint64_t ad = umma::smem_desc(abase + (uint32_t)(2 * ks) * kRows * 16, kRows * 16, 128);
+          // interpolated slices sit in the 128-byte-swizzled layout (8-row groups 1024 B apart, +32 B per
+          // K step inside the atom), everything else in the canonical one
+          const uint64_t ad = (layer1 && (k0c < P.c_known || early))
+                                  ? umma::smem_desc_sw128(abase + (uint32_t)ks * 32, 1024)
+                                  : umma::smem_desc(abase + (uint32_t)(2 * ks) * kRows * 16, kRows * 16, 128);
           const uint64_t bd = umma::smem_desc(w_addr + s * kWVecs * 16 + (uint32_t)(2 * ks) * kWidth * 16,
                                               kWidth * 16, 128);
           const uint32_t acc = layer1 ? ((c | ks) != 0) : (((c - nk1) | ks) != 0);
@@ -364,7 +399,7 @@ fp_mlp_kernel(const FpParams P) {
         mbar_wait(mdone0 + 8 * s, (g >> 1) & 1);
         umma::fence_after_sync();
 #pragma unroll 1
-        for (int c0 = half * (kWidth / 2); c0 < (half + 1) * (kWidth / 2); c0 += 32) {
+        for (int c0 = half * (kWidth / kParts); c0 < (half + 1) * (kWidth / kParts); c0 += 32) {
           uint32_t v[32];
           umma::ld_32x32b_x32(tmem_d1 + lane_addr + (uint32_t)c0, v);
           umma::wait_ld();
@@ -391,10 +426,14 @@ fp_mlp_kernel(const FpParams P) {
       const uint32_t g = gchunk - 1, s = g & 1;
       mbar_wait(mdone0 + 8 * s, (g >> 1) & 1);
       umma::fence_after_sync();
-      float *opm = P.out_pm ? P.out_pm + ((size_t)scene * P.n + j) * kWidth : nullptr;
+      // channel-major: lanes = consecutive points, one full line per warp store.  Point-major: the 32 x 32
+      // block a warp just read is turned through a 4 KB shared-memory patch (the weight stages are idle
+      // now; 16-byte chunks swizzled by row & 7, conflict-free both ways) so that a quarter warp stores 128
+      // contiguous bytes of one row -- a lane-per-row store would touch 32 lines per instruction.
       float *ocm = P.out_cm + (size_t)scene * kWidth * P.n + j;
+      float4 *patch = reinterpret_cast<float4 *>(w_st) + warp * 256;
 #pragma unroll 1
-      for (int c0 = half * (kWidth / 2); c0 < (half + 1) * (kWidth / 2); c0 += 32) {
+      for (int c0 = half * (kWidth / kParts); c0 < (half + 1) * (kWidth / kParts); c0 += 32) {
         uint32_t v[32];
         umma::ld_32x32b_x32(tmem_d2 + lane_addr + (uint32_t)c0, v);
         umma::wait_ld();
@@ -404,11 +443,21 @@ fp_mlp_kernel(const FpParams P) {
         if (live) {
 #pragma unroll
           for (int e = 0; e < 32; ++e) ocm[(size_t)(c0 + e) * P.n] = o[e];     // lanes = consecutive points
-          if (opm) {
+        }
+        if (P.out_pm) {
 #pragma unroll
-            for (int e = 0; e < 32; e += 4)
-              *reinterpret_cast<float4 *>(opm + c0 + e) = make_float4(o[e], o[e + 1], o[e + 2], o[e + 3]);
+          for (int e = 0; e < 8; ++e)
+            patch[lane * 8 + (e ^ (lane & 7))] = make_float4(o[4 * e], o[4 * e + 1], o[4 * e + 2], o[4 * e + 3]);
+          __syncwarp();
+#pragma unroll
+          for (int p = 0; p < 8; ++p) {
+            const int rr = p * 4 + rq;                                          // row of this warp's 32
+            const int jj = row0 + quarter * 32 + rr;
+            const float4 t = patch[rr * 8 + (q8 ^ (rr & 7))];
+            if (jj < P.n)
+              *reinterpret_cast<float4 *>(P.out_pm + ((size_t)scene * P.n + jj) * kWidth + c0 + q8 * 4) = t;
           }
+          __syncwarp();
         }
       }
     }
@@ -451,16 +500,20 @@ int fp_forward_dispatch(int b, int n, int m, int c_known, int c_skip, const floa
   if (skip16 && ((skip16_stride % 8) || skip16_stride < c_skip || (reinterpret_cast<uintptr_t>(skip16) & 15)))
     return set_error(BQA_ERR_INVALID_ARG, "fp_mlp: skip16 rows must be 16-byte aligned and hold c_skip values");
   P.w = (const uint4 *)w; P.b1 = b1; P.b2 = b2; P.out_cm = out_cm; P.out_pm = out_pm; P.fp16 = fp16;
+  P.wide = (known_stride % 8 == 0) && !(reinterpret_cast<uintptr_t>(known_feat) & 31);
   P.tiles_per_scene = ceil_div(n, kRows);
   P.num_tiles = b * P.tiles_per_scene;
   const size_t smem = 16 * (2 * (size_t)(kChunk / 8 * kRows) + 2 * (size_t)(kChunk / 8 * kWidth) +
                             (size_t)(kWidth / 8 * kRows)) + 4 * (kKnownTile * 4 + 2 * kWidth) +
-                      sizeof(NnRow) * kRows + 4 * 6 * kRows + 32 + 16;
+                      sizeof(NnRow) * kRows + 4 * 6 * kRows * (kParts - 1) + 32 + 16 + 1024;
   BQA_CUDA(cudaFuncSetAttribute(fp_mlp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int dev = 0, sms = 148;
   BQA_CUDA(cudaGetDevice(&dev));
   BQA_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   const int grid = min(P.num_tiles, sms);
+#ifdef BQA_SA_TRACE
+  P.dbg = getenv("BQA_FP_DBG") ? atoi(getenv("BQA_FP_DBG")) : 0;
+#endif
   fp_mlp_kernel<<<grid, kThreads, smem, stream>>>(P);
 #ifdef BQA_SA_TRACE
   {

@@ -24,6 +24,13 @@ __device__ __forceinline__ uint64_t smem_desc(uint32_t smem_addr, uint32_t lbo_b
          ((uint64_t)((sbo_bytes >> 4) & 0x3fffu) << 32) | (1ull << 46);
 }
 
+// K-major operand in the 128-byte-swizzle layout (row pitch 128 B, 16-byte chunk index ^ (row & 7), 8-row groups
+// `sbo_bytes` apart, buffer 1024-byte aligned): layout type 2 in [61,64); the leading offset is unused (1).
+__device__ __forceinline__ uint64_t smem_desc_sw128(uint32_t smem_addr, uint32_t sbo_bytes) {
+  return (uint64_t)((smem_addr >> 4) & 0x3fffu) | (1ull << 16) |
+         ((uint64_t)((sbo_bytes >> 4) & 0x3fffu) << 32) | (1ull << 46) | (2ull << 61);
+}
+
 // 32-bit instruction descriptor for kind::f16 with 16-bit A/B (both K-major) and FP32 D:
 //  [4,6) D format = 1 (f32), [7,10) A format, [10,13) B format (0 = f16, 1 = bf16),
 //  bit 15 / 16 = A / B major (0 = K), [17,23) N >> 3, [24,29) M >> 4.

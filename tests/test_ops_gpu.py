@@ -539,3 +539,32 @@ def test_ball_query_slices_equal_one_call():
         N.call("bqa_ball_query_slice", b, n, m, lo, cnt, ctypes.c_float(r), ns, N.ptr(centres), N.ptr(xyz),
                N.ptr(idx), N.ptr(work) if nbytes else ctypes.c_void_p(0), N.stream_ptr(xyz.device))
     assert torch.equal(idx, want)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("b,n,c", [(2, 1000, 7), (1, 257, 7), (3, 256, 1), (2, 513, 13), (2, 300, 29), (2, 300, 132)])
+@pytest.mark.parametrize("prec", ["fp16", "bf16"])
+def test_point_major_16_of_the_input_cloud(b, n, c, prec):
+    """The 16-bit point-major twin of the backbone's input features (the SA1 gather source), converted row-wise
+    from the (B, N, 3 + C) cloud: narrow rows through the staged kernel (whole blocks of 256 rows and ragged
+    tails), wide rows one 16-byte chunk per thread.  Bit-equal to torch's own round-to-nearest conversion."""
+    from bridgeqa_b200 import fused
+    old = fused.precision()
+    fused.set_precision(prec)
+    try:
+        g = torch.Generator().manual_seed(c * 1000 + n)
+        cloud = (torch.randn(b, n, 3 + c, generator=g) * 3).cuda()
+        feats = cloud[..., 3:].transpose(1, 2)                 # (B, C, N) view, as the backbone makes it
+        feats._bqa_cloud = cloud
+        twin = fused.point_major_16(feats)
+        stride = (c + 7) // 8 * 8
+        assert twin.shape == (b, n, stride) and twin.dtype == torch.int16
+        dt = torch.float16 if prec == "fp16" else torch.bfloat16
+        want = torch.zeros(b, n, stride, dtype=dt, device="cuda")
+        want[..., :c] = cloud[..., 3:].to(dt)
+        assert torch.equal(twin, want.view(torch.int16))
+        # and the transpose-convert kernel used when the features are a tensor of their own
+        twin2 = fused.point_major_16(feats.contiguous())
+        assert torch.equal(twin2, want.view(torch.int16))
+    finally:
+        fused.set_precision(old)
