@@ -170,6 +170,10 @@ FUSED_SA_CASES = [
     (3, 512, 256, 64, 1.2, 16, [128, 128, 256]),
     (2, 1024, 256, 256, 0.3, 16, [128, 128, 128]),
     (1, 3000, 13, 8, 0.5, 128, [64, 64, 128]),
+    # feature chunk counts that do not fill the 8-chunk swizzle blocks of the operand buffer (10 = 8 + 2) and a
+    # second pass of 8 chunks (24 = 16 + 8)
+    (1, 2000, 83, 32, 0.5, 32, [128, 128, 256]),
+    (1, 2000, 200, 32, 0.5, 32, [128, 128, 256]),
 ]
 
 
