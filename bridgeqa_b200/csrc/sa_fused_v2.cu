@@ -687,41 +687,6 @@ __global__ void rows_to_16_kernel(long long rows, int c, int row_stride, int fir
   reinterpret_cast<uint4 *>(out)[t] = make_uint4(p[0], p[1], p[2], p[3]);
 }
 
-// The same for narrow rows (row_stride <= 32 floats; the backbone's xyz + 7 features = 10): one thread per row
-// would read 4-byte pieces 40 bytes apart -- a line per lane and instruction.  A block stages 256 whole rows
-// with coalesced 16-byte loads and converts from shared memory; 16-byte stores, consecutive per lane.
-constexpr int kNarrowRows = 256;
-__global__ void __launch_bounds__(256)
-rows_to_16_narrow_kernel(long long rows, int c, int row_stride, int first, int stride, int fp16,
-                         const float *__restrict__ in, uint16_t *__restrict__ out) {
-  extern __shared__ float s_rows[];
-  const long long row0 = (long long)blockIdx.x * kNarrowRows;
-  const int nrows = (int)min((long long)kNarrowRows, rows - row0);
-  const int nfloats = nrows * row_stride;                 // row0 * row_stride is a multiple of 4 (256 rows per block)
-  const float *src = in + (size_t)row0 * row_stride;
-  for (int i = threadIdx.x * 4; i < nfloats; i += blockDim.x * 4) {
-    if (i + 4 <= nfloats) {
-      *reinterpret_cast<float4 *>(s_rows + i) = __ldg(reinterpret_cast<const float4 *>(src + i));
-    } else {
-      for (int e = i; e < nfloats; ++e) s_rows[e] = __ldg(src + e);
-    }
-  }
-  __syncthreads();
-  const int per_row = stride / 8;
-  for (int t = threadIdx.x; t < nrows * per_row; t += blockDim.x) {
-    const int r = t / per_row, k0 = (t % per_row) * 8;
-    const float *row = s_rows + r * row_stride + first;
-    uint32_t p[4];
-#pragma unroll
-    for (int e = 0; e < 4; ++e) {
-      const float lo = k0 + 2 * e < c ? row[k0 + 2 * e] : 0.f;
-      const float hi = k0 + 2 * e + 1 < c ? row[k0 + 2 * e + 1] : 0.f;
-      p[e] = pack2h(lo, hi, fp16);
-    }
-    reinterpret_cast<uint4 *>(out)[(size_t)row0 * per_row + t] = make_uint4(p[0], p[1], p[2], p[3]);
-  }
-}
-
 template <int C1, int C2, int C3, int S, int E>
 int launch_v2(Sa2Params P, cudaStream_t stream) {
   using L = Sa2Layout<C1, C2, C3>;
@@ -814,12 +779,6 @@ int to_point_major_16_dispatch(int b, int c, int n, int stride, int fp16, const 
 int rows_to_16_dispatch(long long rows, int c, int row_stride, int first, int stride, int fp16, const float *in,
                         void *out, cudaStream_t stream) {
   const long long total = rows * (stride / 8);
-  if (row_stride <= 32 && !(reinterpret_cast<uintptr_t>(in) & 15)) {
-    rows_to_16_narrow_kernel<<<(unsigned)ceil_div_ll(rows, kNarrowRows), 256, kNarrowRows * row_stride * sizeof(float),
-                               stream>>>(rows, c, row_stride, first, stride, fp16, in, (uint16_t *)out);
-    count_launch();
-    return check_launch("rows_to_16_narrow_kernel");
-  }
   rows_to_16_kernel<<<(unsigned)ceil_div_ll(total, 256), 256, 0, stream>>>(rows, c, row_stride, first, stride, fp16,
                                                                           in, (uint16_t *)out);
   count_launch();

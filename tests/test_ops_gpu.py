@@ -546,8 +546,8 @@ def test_ball_query_slices_equal_one_call():
 @pytest.mark.parametrize("prec", ["fp16", "bf16"])
 def test_point_major_16_of_the_input_cloud(b, n, c, prec):
     """The 16-bit point-major twin of the backbone's input features (the SA1 gather source), converted row-wise
-    from the (B, N, 3 + C) cloud: narrow rows through the staged kernel (whole blocks of 256 rows and ragged
-    tails), wide rows one 16-byte chunk per thread.  Bit-equal to torch's own round-to-nearest conversion."""
+    from the (B, N, 3 + C) cloud, one 16-byte chunk per thread (narrow and wide rows, ragged row counts, zero
+    padding of the last chunk).  Bit-equal to torch's own round-to-nearest conversion."""
     from bridgeqa_b200 import fused
     old = fused.precision()
     fused.set_precision(prec)
