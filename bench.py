@@ -619,6 +619,20 @@ def main():
         barrier()
     kern = kt.summary()
     kernel_pass_ms = kp0.elapsed_time(kp1)
+    # what an event pair around a C-ABI call reads when the call launches nothing (zero rows): the host-side gap
+    # between the two records under eager issue.  Rows of kernels[] shorter than a few times this carry it.
+    import ctypes as _ct
+    floor = []
+    for _ in range(21):
+        fa, fb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        fa.record()
+        _native.call("bqa_rows_to_16", _ct.c_longlong(0), 7, 10, 3, 8, 1, None, None,
+                     _native.stream_ptr(device))
+        fb.record()
+        torch.cuda.synchronize()
+        floor.append(fa.elapsed_time(fb))
+    event_pair_floor_ms = sorted(floor)[len(floor) // 2]
     launches = _native.launch_count() - launches0   # == kernel nodes the graph replays for K steps
     if not args.no_graph:
         net.enable_cuda_graph(True, bind_inputs=True)
@@ -687,6 +701,16 @@ def main():
 
     e2e_run(2 * NB)
     barrier()
+    # the host link alone: the same pinned input copied back to back, no kernels (explains an end-to-end
+    # number that is bound by the copy: the boxes of the pool differ by 2x here)
+    ca, cb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with torch.cuda.stream(copy_in):
+        ca.record(copy_in)
+        for i in range(8):
+            dev_buf[i % NB].copy_(host_e2e[i % ROT], non_blocking=True)
+        cb.record(copy_in)
+    copy_in.synchronize()
+    h2d_alone_gbps = 8 * h2d_bytes / (ca.elapsed_time(cb) * 1e-3) / 1e9
     d2h_bytes = sum(t.numel() * t.element_size() for t in out_host.values())
     e0 = torch.cuda.Event(enable_timing=True)
     e1 = torch.cuda.Event(enable_timing=True)
@@ -800,6 +824,8 @@ def main():
                        "note": "same K steps with one batch in flight (latency variant of the sampling kernel) = latency of a batch"},
             "e2e": {"value": scenes / (e2e_ms / 1e3), "unit": UNIT, "ms_per_step": e2e_ms / args.steps,
                     "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
+                    "h2d_alone_gb_per_s": round(h2d_alone_gbps, 2),
+                    "h2d_alone_ms_per_step": round(h2d_bytes / h2d_alone_gbps / 1e6, 4),
                     "input": ("staging.StagedCloud: fp32 xyz + 16-bit point-major features (pinned host)"
                               if args.e2e_input == "staged16" else "(B,N,3+C) fp32 cloud (pinned host)"),
                     "read_back": {k_: list(v_.shape) + [str(v_.dtype)] for k_, v_ in out_host.items()}},
@@ -808,8 +834,12 @@ def main():
             "gpu_launches": launches,
             "host_issue_ms_per_step": round(host_issue_ms, 3),
             "kernel_pass": {"ms_per_step": round(kernel_pass_ms / args.steps, 4),
+                            "event_pair_floor_ms": round(event_pair_floor_ms, 4),
                             "note": "kernels[] and roofline come from a second pass of the same K steps with "
-                                    "CUDA events around every C-ABI call; shares are relative to that pass"},
+                                    "CUDA events around every C-ABI call; shares are relative to that pass.  "
+                                    "Issued eagerly, the host leaves event_pair_floor_ms between the two records even "
+                                    "when nothing is launched: rows of a few hundredths of a ms are upper bounds "
+                                    "(ncu durations of the same kernels: profiles/r2_kernels_ncu.json)"},
             "roofline": roofline,
             "kernels": kernels,
             "clocks": clk,
