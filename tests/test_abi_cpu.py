@@ -58,6 +58,7 @@ def test_sass_is_sm100a_and_uses_cluster_and_bulk_copy():
     assert "LDTM" in sass, "tcgen05.ld missing"
     assert "UTCBAR" in sass, "tcgen05.commit missing"
     assert "LDGSTS" in sass, "cp.async missing"
+    assert "LDG.E.ENL2.256" in sass, "256-bit neighbour-row loads of the FP kernel missing"
 
 
 def test_sass_histogram_in_profiles_matches_the_built_library():
