@@ -163,10 +163,7 @@ struct Sa2Layout {
   static constexpr int kTailVecs = 2 * kRows;
   static constexpr int kTmemCols = (C1 + C2 > C3 ? C1 + C2 : C3);     // per slot: D1 | D2, D3T aliases
   static_assert(kTmemCols == 128 || kTmemCols == 256, "TMEM columns per slot");
-  // feature chunks of one pass, in whole K blocks of 8 chunks (64 channels): [block][128 rows][128 B], swizzled
-  static __host__ __device__ int main_vecs(int n_main) {
-    return ((n_main < kPassChunks ? n_main : kPassChunks) + 7) / 8 * 8 * kRows;
-  }
+  static __host__ __device__ int main_vecs(int n_main) { return (n_main < kPassChunks ? n_main : kPassChunks) * kRows; }
   static __host__ __device__ int slot_vecs(int n_main, int alias) {
     const int mv = main_vecs(n_main);
     return kTailVecs + (alias ? (mv > kXVecs ? mv : kXVecs) : mv + kXVecs);
@@ -193,10 +190,7 @@ sa_v2_kernel(const Sa2Params P) {
   constexpr uint32_t kTmemTotal = (uint32_t)(S * L::kTmemCols);
   static_assert(kTmemTotal <= 512 && (kTmemTotal & (kTmemTotal - 1)) == 0, "TMEM budget");
 
-  // The kernel has no static shared memory, so the dynamic window starts 1024-byte aligned, and every region
-  // below is a multiple of 1024 bytes: the swizzled feature buffers (128-byte atoms, 8-row groups) stay aligned.
-  extern __shared__ __align__(1024) unsigned char smem_raw[];
-  if (smem_u32(smem_raw) & 1023u) __trap();
+  extern __shared__ __align__(128) unsigned char smem_raw[];
   uint4 *w1s = reinterpret_cast<uint4 *>(smem_raw);                   // [k1pad/8][C1]
   uint4 *w2s = w1s + (size_t)(P.k1pad / 8) * C1;                      // [C1/8 + 2][C2]  (last K step: bias)
   uint4 *w3s = w2s + (size_t)(C1 / 8 + 2) * C2;                       // [C2/8][C3]
@@ -419,28 +413,25 @@ sa_v2_kernel(const Sa2Params P) {
       if (pw == 0) { V2_TRACE(1, 200 + k * 1000) }
       for (int pass = 0; pass < P.passes; ++pass) {
         if (n_main > 0) {
-          // ---- feature chunks [16 pass, ...): a quarter warp copies 128 contiguous bytes (8 chunks) of ONE
-          // source row per instruction (one or two lines; a lane-per-row mapping costs a line per lane), into
-          // the 128-byte-swizzled K-major layout: K block kb = [128 rows][128 B], chunk ^ (row & 7) -- the 8
-          // lanes of a row land in 8 different bank groups.
+          // ---- feature chunks [16 pass, ...): 8 rows x 4 chunks (64 contiguous bytes of each row) per
+          // warp instruction; a quarter warp writes 128 contiguous bytes of one chunk column.
           // The buffer has been released u * passes + pass times when it may be written (a fresh
           // barrier passes a wait on parity 1).
           wait_bar(smem_u32(&bars[s].main_free), (uint32_t)(((u * P.passes + pass) & 1) ^ 1), 21);
           if (pw == 0) { V2_TRACE(1, 203 + k * 1000 + 10 * pass) }
           const int ch0 = pass * kPassChunks;
           const int ch1 = min(n_main, ch0 + kPassChunks);
-          const int q8 = lane & 7;
-          const uint32_t dst_base = smem_u32(slot_main(s));
-          const uint16_t *fbase = P.feat16 + (size_t)scene * P.n * P.stride16 + (size_t)(ch0 + q8) * 8;
+          const uint32_t dst_base = smem_u32(slot_main(s)) + (uint32_t)(pw * 32) * 16u;
+          const uint16_t *fbase = P.feat16 + (size_t)scene * P.n * P.stride16 + (size_t)(ch0 + (lane >> 3)) * 8;
+          const uint32_t dcol = (uint32_t)(lane >> 3) * (kRows * 16u);
 #pragma unroll
-          for (int r4 = 0; r4 < 8; ++r4) {
-            const int lrow = r4 * 4 + (lane >> 3);                       // row of this warp
+          for (int r8 = 0; r8 < 4; ++r8) {
+            const int lrow = r8 * 8 + (lane & 7);                        // row of this warp
             const int src_i = __shfl_sync(0xffffffffu, cur.i, lrow);
-            const int trow = pw * 32 + lrow;                             // row of the tile
             const uint16_t *srow = fbase + (size_t)src_i * P.stride16;
-            const uint32_t drow = dst_base + (uint32_t)(trow * 128 + ((q8 ^ (trow & 7)) << 4));
-            for (int cb = ch0 + q8, kb = 0; cb < ch1; cb += 8, ++kb)
-              cp_async_16(drow + (uint32_t)kb * (kRows * 128u), srow + kb * 64);
+            const uint32_t drow = dst_base + (uint32_t)lrow * 16u + dcol;
+            for (int cb = ch0 + (lane >> 3); cb < ch1; cb += 4)
+              cp_async_16(drow + (uint32_t)(cb - ch0 - (lane >> 3)) * (kRows * 16u), srow + (cb - ch0 - (lane >> 3)) * 8);
           }
         }
         if (pass == 0) {
@@ -529,7 +520,7 @@ sa_v2_kernel(const Sa2Params P) {
     const uint32_t tmem = tmem_base + (uint32_t)(s * L::kTmemCols);
     // descriptors of the first K step of every operand; one K step (two 16-byte chunk columns) further is a
     // constant added to the address field (bits [0,14) hold address >> 4)
-    const uint64_t d_main = umma::smem_desc_sw128(smem_u32(slot_main(s)), 1024);   // 8-row groups 1024 B apart
+    const uint64_t d_main = umma::smem_desc(smem_u32(slot_main(s)), kRows * 16, 128);
     const uint64_t d_tail = umma::smem_desc(smem_u32(slot_tail(s)), kRows * 16, 128);
     const uint64_t d_x = umma::smem_desc(smem_u32(slot_x(s)), kRows * 16, 128);
     const uint64_t d_ones = umma::smem_desc(smem_u32(ones), kRows * 16, 128);
@@ -551,12 +542,10 @@ sa_v2_kernel(const Sa2Params P) {
         umma::fence_after_sync();
         V2_TRACE(2, 300 + 10 * s + p)
         const int cnt = min(P.n_main - p * kPassChunks, kPassChunks);      // feature chunks of this pass (even; may be <= 0)
-        uint64_t bd = d_w1 + (uint64_t)(p * (kPassChunks / 2)) * kStepW1;
+        uint64_t ad = d_main, bd = d_w1 + (uint64_t)(p * (kPassChunks / 2)) * kStepW1;
         for (int ks = 0; ks < cnt / 2; ++ks) {
-          // K step ks = 32 bytes of every row: block ks / 4 (16 KB each), +32 B inside the swizzle atom
-          const uint64_t ad = d_main + (uint64_t)((ks >> 2) * ((kRows * 128) >> 4) + (ks & 3) * 2);
           umma::mma_bf16_ss(tmem, ad, bd, idesc1, (p | ks) != 0);
-          bd += kStepW1;
+          ad += kStepRows; bd += kStepW1;
         }
         if (p == P.passes - 1) {
           umma::mma_bf16_ss(tmem, d_tail, d_w1 + (uint64_t)(P.n_main / 2) * kStepW1, idesc1, P.n_main > 0);

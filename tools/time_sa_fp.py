@@ -7,8 +7,9 @@ import os
 from bridgeqa_b200 import detector, synthetic, _native as N
 if os.environ.get("BQA_SO"):
     N.SO_PATH = os.environ["BQA_SO"]            # A/B against another build of the library
-pc = synthetic.make_batch(16, 40000, 7).cuda()
-net = synthetic.fill_state_dict(detector.Pointnet2Backbone(input_feature_dim=7), seed=0).cuda().eval()
+C = int(os.environ.get("BQA_C", "7"))
+pc = synthetic.make_batch(16, 40000, C).cuda()
+net = synthetic.fill_state_dict(detector.Pointnet2Backbone(input_feature_dim=C), seed=0).cuda().eval()
 names = ["bqa_sa_mlp_max_forward_v2", "bqa_fp_mlp_forward"]
 with torch.no_grad():
     for _ in range(3): net({"point_clouds": pc})
