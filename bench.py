@@ -457,7 +457,7 @@ def main():
                     "forward instead of under the previous step's backward")
     ap.add_argument("--torch-bn", action="store_true", help="--mode train: torch BatchNorm/ReLU/max_pool modules "
                     "instead of the sm_100a streaming kernels (the reference's module structure)")
-    ap.add_argument("--in-flight", type=int, default=8,
+    ap.add_argument("--in-flight", type=int, default=12,
                     help="batches in flight (graphs.InFlight): consecutive steps are issued on a ring of this many "
                          "streams so the next batch's sampling chain runs under this batch's SA/FP kernels; 1 = serial")
     ap.add_argument("--bind-cpu", action="store_true",
