@@ -41,6 +41,18 @@
 //    and a named barrier per scene, so two chains share the schedulers): bit-exact; with 128-point runs
 //    2.21 us per iteration for both scenes = 36 SM-ms per batch instead of 40 at 1.8x the latency of a
 //    call; with 64-point runs and two owner slots per lane 2.66 us = 43 SM-ms.  Not worth the latency.
+//  * SEVERAL SAMPLES PER ROUND: take the 8 best run records (two posted per warp, exact up to the first
+//    second-record), let warp j compute -- read-only -- the best of run(c_j) after c_j itself, and certify the
+//    prefix c_1 .. c_s in which no accepted c_j can change run(c_i) (the box rule) and every such U_j ranks below
+//    c_i; then apply the s samples in one pass.  tools/fps_batch_sim.py replays the rule on the CPU: 4.7 samples
+//    per round, sequence identical to the oracle's.  Implemented, bit-exact on every size on the first run
+//    (2047 samples in 506-512 rounds), and SLOWER: 2.99-3.06 ms against 2.50 (phase trace per round, 12.4-13.3k
+//    cycles: box tests 0.7k, the one-pass update 4.5k for ~4 runs per warp plus ~3k at the barrier for the warp
+//    that got 7, posts 0.6k, ranking 40 posts ~1.7k, speculation ~1.5k, certification 0.15k on one warp).  The
+//    reason is the one above: the update of the ~20 runs a sample reaches is ~2.5k warp-instructions either
+//    way and the SM issues at ~55 % of its rate on this dependent code, so only the ~2k instructions of
+//    fold / box test / post per sample can be amortised -- at best ~20 %, which the serial rank + speculate +
+//    certify section (8 of 20 warps busy) eats.  Removed again; the replay tool stays.
 #include <cstdio>
 #include <cstdlib>
 

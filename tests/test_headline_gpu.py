@@ -53,10 +53,10 @@ def _fp32_reference_convs():
     bridgeqa_b200.set_precision("fp16")
 
 
-def _bench_regime_forward(net, pcs, keys):
-    """What bench.py does: one graph per input buffer, forwards submitted through in_flight(4)."""
+def _bench_regime_forward(net, pcs, keys, depth=4):
+    """What bench.py does: one graph per input buffer, forwards submitted through in_flight(depth)."""
     net.enable_cuda_graph(bind_inputs=True)
-    q = net.in_flight(4)
+    q = net.in_flight(depth)
     assert q.lean                                    # throughput variant of the sampling kernel
     outs = []
     for rnd in range(2):                             # second round = pure graph replays
@@ -77,11 +77,15 @@ def test_headline_backbone_16x40000_bench_regime_vs_oracle_and_reference_ext():
     want = modules_cpu.backbone(host.numpy(), _sd_cpu(net))
     keys = ("sa1_inds", "sa2_inds", "fp2_inds", "sa1_xyz", "sa2_xyz", "sa3_xyz", "sa4_xyz", "fp2_xyz",
             "sa1_features", "sa2_features", "sa3_features", "sa4_features", "fp2_features")
-    # four distinct device buffers of the SAME batch in flight at once + a rolled variant, as the bench rotates
+    # twelve distinct device buffers in flight at once (bench.py's default depth): the SAME batch ten times and
+    # a rolled variant twice, as the bench rotates its inputs
     rolled = torch.roll(host, shifts=997, dims=1).contiguous()
-    pcs = [host.cuda(), host.cuda(), rolled.cuda(), host.cuda()]
-    outs = _bench_regime_forward(net, pcs, keys)
-    for got in (outs[0], outs[1], outs[3]):
+    pcs = [rolled.cuda() if i in (2, 7) else host.cuda() for i in range(12)]
+    outs = _bench_regime_forward(net, pcs, keys, depth=12)
+    for i in (3, 5, 8, 11):
+        for k in keys:                                # every copy of the batch in flight: bit-identical results
+            assert torch.equal(outs[i][k], outs[0][k]), (i, k)
+    for got in (outs[0], outs[1]):
         for k in ("sa1_inds", "sa2_inds", "fp2_inds", "sa1_xyz", "sa2_xyz", "sa3_xyz", "sa4_xyz", "fp2_xyz"):
             np.testing.assert_array_equal(got[k].cpu().numpy(), want[k], err_msg=k)
         for k in ("sa1_features", "sa2_features", "sa3_features", "sa4_features", "fp2_features"):
