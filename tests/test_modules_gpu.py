@@ -264,6 +264,30 @@ def test_fused_fp_kernel_matches_unfused_fp32(B, n, m, ck, cs, precision, tol, _
     assert torch.equal(got._bqa_pm, got.transpose(1, 2).contiguous())
 
 
+def test_fused_fp_kernel_known_rows_not_32_byte_aligned(_restore_fused):
+    """The FP kernel reads 32 bytes of a neighbour row per lane with one 256-bit load when the point-major known
+    features allow it; rows that are only 16-byte aligned (a 260-float pitch, first row 16 bytes into the
+    buffer) take two 128-bit loads.  Same bits either way."""
+    bridgeqa_b200.set_precision("fp16")
+    bridgeqa_b200.set_fused(True)
+    B, n, m = 2, 300, 200
+    fp = synthetic.fill_state_dict(pm.PointnetFPModule(mlp=[256 + 128, 256, 256]), seed=22).cuda().eval()
+    xyz = synthetic.make_batch(B, n + m, 0, first_scene=87)[..., :3].contiguous().cuda()
+    unknown, known = xyz[:, :n].contiguous(), xyz[:, n:].contiguous()
+    uf = torch.randn(B, 128, n, device="cuda")
+    kf = torch.randn(B, 256, m, device="cuda")
+    with torch.no_grad():
+        want = fp(unknown, known, uf, kf)                  # contiguous point-major twin: 256-bit loads
+        pitched = torch.zeros(B, m, 260, device="cuda")
+        twin = pitched[..., 4:]                            # (B, m, 256) view, pitch 260 floats, +16 bytes
+        twin.copy_(kf.transpose(1, 2))
+        assert twin.data_ptr() % 32 == 16 and twin.stride(1) % 8 == 4
+        kf2 = kf.clone()
+        kf2._bqa_pm = twin
+        got = fp(unknown, known, uf, kf2)
+    assert torch.equal(got, want)
+
+
 def test_detector_train_step_backward_reaches_every_parameter():
     """configs[3] on one GPU: train-mode forward + backward through gather / group /
     three_interpolate gradient kernels and the MLPs; all parameters get finite gradients and
