@@ -75,8 +75,9 @@ struct __align__(16) Post {      // 32-byte slot
 
 // 27-bit tie key for bs = 512: (bitrev9(k & 511) << 18) | (k >> 9); smaller wins.  k < 2^27.
 __device__ __forceinline__ uint32_t nkey_of(uint32_t k) {
-  const uint32_t key = ((__brev(k & 511u) >> 23) << 18) | (k >> 9);
-  return (~key & 0x7ffffffu) << 5;
+  // (~key & 0x7ffffff) << 5 with key = bitrev9(k & 511) << 18 | k >> 9: the reversed low 9 bits are the top 9
+  // bits of brev(k), and (k >> 9) << 5 = (k >> 4) with its low 5 bits cleared
+  return ((__brev(k) & 0xff800000u) | ((k >> 4) & 0x007fffe0u)) ^ 0xffffffe0u;
 }
 __device__ __forceinline__ uint32_t index_of(uint32_t nk) {
   const uint32_t key = ~(nk >> 5) & 0x7ffffffu;
