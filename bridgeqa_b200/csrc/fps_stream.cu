@@ -180,8 +180,11 @@ __device__ __forceinline__ void stream_pair(bool has_b, const int (&r)[2], const
 #endif
 }
 
+// Launch bound: 64-point runs need at most 27 warps (835 runs, ~53k points).  Compiled for 1024 threads the kernel
+// is capped at 64 registers and measures 2.7 % slower (2.484 vs 2.419 ms at 16 x 40000) than with this bound
+// (68 registers); a bound of 640 -- what a 40k-point scene launches -- gave 69 registers and 2.478 ms.
 template <int PPL>
-__global__ void __launch_bounds__(1024, 1)
+__global__ void __launch_bounds__(PPL == 2 ? 864 : 1024, 1)
 fps_stream_kernel(int n, int m, int nr, const float4 *__restrict__ sorted_all,
                   const float *__restrict__ xyz_all, int *__restrict__ idx_all,
                   float *__restrict__ new_xyz_all) {
@@ -356,7 +359,7 @@ int stream_warps(int nr) {
   static const int forced = [] { const char *e = getenv("BQA_FPS_STREAM_WARPS"); return e ? atoi(e) : 0; }();
   int w = ceil_div(nr, 32);
   if (w < 8) w = 8;
-  if (forced && forced >= w && forced <= 32) w = forced;
+  if (forced && forced >= w && forced <= 27) w = forced;   // (27 warps: the launch bound of the 64-point-run kernel)
   return w;
 }
 
